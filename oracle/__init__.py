@@ -1,0 +1,226 @@
+"""oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes bindings for the two CPU checkers of the Frangi hot path:
+
+* ``Oracle``     -> oracle/liboracle.so, our C restatement (frangi_oracle.c,
+                    seeds_oracle.c) of pnr-vaa3d/frangi.cpp and seed.cpp:556-791.
+* ``Reference``  -> oracle/_ref/libpnr_ref.so, the UNMODIFIED reference sources
+                    compiled in place from /root/reference (oracle/Makefile,
+                    ref_wrap.cpp).  Present only where it was built (the build
+                    container) or where the prebuilt file travelled (gpurun).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this package.  pnr_b200/ never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "liboracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libpnr_ref.so")
+
+_u8p = C.POINTER(C.c_uint8)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+
+
+def build(verbose: bool = False) -> None:
+    """Compile liboracle.so and, when /root/reference is present, _ref/libpnr_ref.so."""
+    out = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout, out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def _check_vol(I):
+    I = np.ascontiguousarray(I, dtype=np.uint8)
+    if I.ndim != 3:
+        raise ValueError("volume must be [l][h][w] uint8")
+    l, h, w = I.shape
+    return I, w, h, l
+
+
+class Oracle:
+    """Our C restatement.  Volumes are numpy arrays shaped [l][h][w] (x fastest)."""
+
+    def __init__(self, path: str = ORACLE_SO):
+        if not os.path.exists(path):
+            build()
+        self.lib = L = C.CDLL(path)
+        L.oracle_gauss_radius.restype = C.c_int
+        L.oracle_gauss_radius.argtypes = [C.c_float]
+        L.oracle_gauss_taps.restype = None
+        L.oracle_gauss_taps.argtypes = [C.c_float, C.c_int, _f32p]
+        L.oracle_imgaussian.restype = C.c_int
+        L.oracle_imgaussian.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _f32p]
+        L.oracle_hessian3d.restype = C.c_int
+        L.oracle_hessian3d.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float] + [_f32p] * 6
+        L.oracle_eigen3.restype = None
+        L.oracle_eigen3.argtypes = [_f64p, _f64p, _f64p]
+        L.oracle_frangi3d.restype = C.c_int
+        L.oracle_frangi3d.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_float,
+                                      C.c_float, C.c_float, C.c_float, C.c_int,
+                                      _f32p, _f32p, _f32p, _u8p, _u8p, _u8p, _u8p, _f32p]
+        L.oracle_vesselness_stage.restype = None
+        L.oracle_vesselness_stage.argtypes = [_f32p] * 6 + [C.c_int64, C.c_float, C.c_float, C.c_float,
+                                                            C.c_int, _f32p, _f32p, _f64p]
+        L.oracle_j_to_j8.restype = None
+        L.oracle_j_to_j8.argtypes = [_f32p, C.c_int64, C.c_float, C.c_float, _u8p]
+        L.oracle_extract_seeds.restype = C.c_long
+        L.oracle_extract_seeds.argtypes = [C.c_double, _u8p, C.c_int, C.c_int, C.c_int,
+                                           _u8p, _u8p, _u8p, _f32p, C.c_long]
+
+    def gauss_taps(self, sigma: float):
+        r = self.lib.oracle_gauss_radius(sigma)
+        t = np.zeros(2 * r + 1, np.float32)
+        self.lib.oracle_gauss_taps(sigma, r, _p(t, _f32p))
+        return r, t
+
+    def imgaussian(self, I, sigma, zdist):
+        I, w, h, l = _check_vol(I)
+        F = np.empty(I.shape, np.float32)
+        rc = self.lib.oracle_imgaussian(_p(I, _u8p), w, h, l, sigma, zdist, _p(F, _f32p))
+        if rc:
+            raise RuntimeError(f"oracle_imgaussian rc={rc}")
+        return F
+
+    def hessian3d(self, I, sigma, zdist):
+        """Returns dict with keys Dzz,Dyy,Dyz,Dxx,Dxy,Dxz (reference argument order)."""
+        I, w, h, l = _check_vol(I)
+        names = ["Dzz", "Dyy", "Dyz", "Dxx", "Dxy", "Dxz"]
+        D = [np.empty(I.shape, np.float32) for _ in names]
+        rc = self.lib.oracle_hessian3d(_p(I, _u8p), w, h, l, sigma, zdist, *[_p(d, _f32p) for d in D])
+        if rc:
+            raise RuntimeError(f"oracle_hessian3d rc={rc}")
+        return dict(zip(names, D))
+
+    def eigen3(self, A):
+        A = np.ascontiguousarray(A, np.float64).reshape(9)
+        V = np.empty(9, np.float64)
+        d = np.empty(3, np.float64)
+        self.lib.oracle_eigen3(_p(A, _f64p), _p(V, _f64p), _p(d, _f64p))
+        return V.reshape(3, 3), d
+
+    def frangi3d(self, I, sigmas, zdist=2.0, alpha=0.5, beta=0.5, Cc=500.0, blackwhite=False,
+                 want_scale=True, want_dir=True):
+        I, w, h, l = _check_vol(I)
+        s = np.ascontiguousarray(sigmas, np.float32)
+        J = np.empty(I.shape, np.float32)
+        V = [np.empty(I.shape, np.uint8) for _ in range(3)]
+        sc = np.zeros(I.shape, np.uint8) if want_scale else None
+        dr = np.zeros((3,) + I.shape, np.float32) if want_dir else None
+        lo, hi = C.c_float(), C.c_float()
+        rc = self.lib.oracle_frangi3d(_p(I, _u8p), w, h, l, _p(s, _f32p), len(s), zdist, alpha, beta, Cc,
+                                      int(blackwhite), _p(J, _f32p), C.byref(lo), C.byref(hi),
+                                      _p(V[0], _u8p), _p(V[1], _u8p), _p(V[2], _u8p),
+                                      _p(sc, _u8p), _p(dr, _f32p))
+        if rc:
+            raise RuntimeError(f"oracle_frangi3d rc={rc}")
+        return dict(J=J, Jmin=lo.value, Jmax=hi.value, Vx=V[0], Vy=V[1], Vz=V[2], scale=sc, dir=dr)
+
+    def vesselness_stage(self, D, alpha=0.5, beta=0.5, Cc=500.0, blackwhite=False, want_lambda=False):
+        """D: dict Dxx,Dxy,Dxz,Dyy,Dyz,Dzz of equal-shape float32 arrays."""
+        arrs = [np.ascontiguousarray(D[k], np.float32) for k in ("Dxx", "Dxy", "Dxz", "Dyy", "Dyz", "Dzz")]
+        n = arrs[0].size
+        v = np.empty(arrs[0].shape, np.float32)
+        dr = np.empty((3,) + arrs[0].shape, np.float32)
+        lam = np.empty(arrs[0].shape + (3,), np.float64) if want_lambda else None
+        self.lib.oracle_vesselness_stage(*[_p(a, _f32p) for a in arrs], n, alpha, beta, Cc, int(blackwhite),
+                                         _p(v, _f32p), _p(dr, _f32p), _p(lam, _f64p))
+        return v, dr, lam
+
+    def j_to_j8(self, J, Jmin, Jmax):
+        J = np.ascontiguousarray(J, np.float32)
+        out = np.empty(J.shape, np.uint8)
+        self.lib.oracle_j_to_j8(_p(J, _f32p), J.size, Jmin, Jmax, _p(out, _u8p))
+        return out
+
+    def extract_seeds(self, tolerance, J8, Vx, Vy, Vz):
+        J8, w, h, l = _check_vol(J8)
+        Vx, Vy, Vz = (np.ascontiguousarray(v, np.uint8) for v in (Vx, Vy, Vz))
+        cap = max(1024, J8.size // 8)
+        out = np.empty((cap, 6), np.float32)
+        n = self.lib.oracle_extract_seeds(tolerance, _p(J8, _u8p), w, h, l, _p(Vx, _u8p), _p(Vy, _u8p),
+                                          _p(Vz, _u8p), _p(out, _f32p), cap)
+        if n < 0 or n > cap:
+            raise RuntimeError(f"oracle_extract_seeds returned {n} (cap {cap})")
+        return out[:n].copy()
+
+
+class Reference:
+    """The unmodified reference (compiled in place).  Same conventions as Oracle."""
+
+    def __init__(self, path: str = REF_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not built: run `make -C oracle ref` where /root/reference exists")
+        self.lib = L = C.CDLL(path)
+        L.ref_imgaussian.restype = None
+        L.ref_imgaussian.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _f32p]
+        L.ref_hessian3d.restype = None
+        L.ref_hessian3d.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float] + [_f32p] * 6
+        L.ref_eigen3.restype = None
+        L.ref_eigen3.argtypes = [_f64p, _f64p, _f64p]
+        L.ref_frangi3d.restype = None
+        L.ref_frangi3d.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_float,
+                                   C.c_float, C.c_float, C.c_float, C.c_int,
+                                   _f32p, _f32p, _f32p, _u8p, _u8p, _u8p]
+        L.ref_extract_seeds.restype = C.c_long
+        L.ref_extract_seeds.argtypes = [C.c_double, _u8p, C.c_int, C.c_int, C.c_int,
+                                        _u8p, _u8p, _u8p, _f32p, C.c_long]
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_SO)
+
+    def imgaussian(self, I, sigma, zdist):
+        I, w, h, l = _check_vol(I)
+        F = np.empty(I.shape, np.float32)
+        self.lib.ref_imgaussian(_p(I, _u8p), w, h, l, sigma, zdist, _p(F, _f32p))
+        return F
+
+    def hessian3d(self, I, sigma, zdist):
+        I, w, h, l = _check_vol(I)
+        names = ["Dzz", "Dyy", "Dyz", "Dxx", "Dxy", "Dxz"]
+        D = [np.empty(I.shape, np.float32) for _ in names]
+        self.lib.ref_hessian3d(_p(I, _u8p), w, h, l, sigma, zdist, *[_p(d, _f32p) for d in D])
+        return dict(zip(names, D))
+
+    def eigen3(self, A):
+        A = np.ascontiguousarray(A, np.float64).reshape(9)
+        V = np.empty(9, np.float64)
+        d = np.empty(3, np.float64)
+        self.lib.ref_eigen3(_p(A, _f64p), _p(V, _f64p), _p(d, _f64p))
+        return V.reshape(3, 3), d
+
+    def frangi3d(self, I, sigmas, zdist=2.0, alpha=0.5, beta=0.5, Cc=500.0, blackwhite=False):
+        I, w, h, l = _check_vol(I)
+        s = np.ascontiguousarray(sigmas, np.float32)
+        J = np.empty(I.shape, np.float32)
+        V = [np.empty(I.shape, np.uint8) for _ in range(3)]
+        lo, hi = C.c_float(), C.c_float()
+        self.lib.ref_frangi3d(_p(I, _u8p), w, h, l, _p(s, _f32p), len(s), zdist, alpha, beta, Cc,
+                              int(blackwhite), _p(J, _f32p), C.byref(lo), C.byref(hi),
+                              _p(V[0], _u8p), _p(V[1], _u8p), _p(V[2], _u8p))
+        return dict(J=J, Jmin=lo.value, Jmax=hi.value, Vx=V[0], Vy=V[1], Vz=V[2])
+
+    def extract_seeds(self, tolerance, J8, Vx, Vy, Vz):
+        J8, w, h, l = _check_vol(J8)
+        Vx, Vy, Vz = (np.ascontiguousarray(v, np.uint8) for v in (Vx, Vy, Vz))
+        cap = max(1024, J8.size // 8)
+        out = np.empty((cap, 6), np.float32)
+        n = self.lib.ref_extract_seeds(tolerance, _p(J8, _u8p), w, h, l, _p(Vx, _u8p), _p(Vy, _u8p),
+                                       _p(Vz, _u8p), _p(out, _f32p), cap)
+        if n < 0 or n > cap:
+            raise RuntimeError(f"ref_extract_seeds returned {n} (cap {cap})")
+        return out[:n].copy()
