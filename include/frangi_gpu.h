@@ -1,0 +1,155 @@
+/*
+ * frangi_gpu.h -- C-ABI of the B200-native multi-scale 3-D Frangi filter.
+ *
+ * This is the drop-in boundary for the one hot path of miroslavradojevic/pnr
+ * that this library replaces: Frangi::frangi3d and the stages under it
+ * (pnr-vaa3d/frangi.h:33, frangi.cpp:152-289 with hessian3d :291-390,
+ * imgaussian :647-784, eigen_decomposition :1269-1493).  The reference has no
+ * FFI of its own (it is a single C++ plugin); the binding a maintainer adds is
+ * the Frangi class shim in pnr_b200/csrc/frangi.h, whose frangi3d forwards to
+ * frangi_gpu_create / frangi_gpu_run / frangi_gpu_destroy.
+ *
+ * Conventions: extern "C", plain pointers and sizes, return 0 on success or a
+ * FRANGI_GPU_E* code (message via frangi_gpu_last_error), no C++ exceptions
+ * cross the boundary, the caller owns every host buffer, the handle owns all
+ * device memory, streams and NCCL communicators, one handle is used by one
+ * thread at a time.  Volumes are x-fastest: index = z*w*h + y*w + x
+ * (frangi.cpp:307).  There is no CPU fallback: every entry point that computes
+ * fails with FRANGI_GPU_ECUDA when no sm_100 device is usable.
+ */
+#ifndef FRANGI_GPU_H
+#define FRANGI_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct frangi_gpu frangi_gpu_t;
+
+enum {
+    FRANGI_GPU_OK = 0,
+    FRANGI_GPU_EINVAL = 1, /* bad argument (dims < 2, nsig < 1, sigma out of range, ...) */
+    FRANGI_GPU_ECUDA = 2,  /* CUDA runtime / driver failure, or no usable device */
+    FRANGI_GPU_ENOMEM = 3, /* device or host allocation failed */
+    FRANGI_GPU_ENCCL = 4,  /* NCCL unavailable or failed */
+    FRANGI_GPU_ESTATE = 5  /* call not valid for this handle (e.g. outputs not requested) */
+};
+
+/* flags for frangi_gpu_create* */
+enum {
+    /* Gaussian passes use fused multiply-add instead of the reference's separate
+     * float32 multiply and add (frangi.cpp:694,729,762).  Faster; the smoothed
+     * volume is then no longer bit-identical to the reference's, the final
+     * outputs stay within the tolerances of BASELINE.json. */
+    FRANGI_GPU_FLAG_FMA_SMOOTHING = 1,
+    /* keep an unquantised float32 direction (3 planar volumes x,y,z) */
+    FRANGI_GPU_FLAG_DIR_F32 = 2,
+    /* keep the arg-max scale index per voxel (uint8) */
+    FRANGI_GPU_FLAG_SCALE_IDX = 4
+};
+
+/* ---- whole-volume handle, one process driving ndev devices ---------------
+ * Replaces: Frangi::Frangi(sigs, zdist, alpha, beta, C, beta_one, beta_two)
+ * (frangi.h:24, frangi.cpp:35-56) plus the scratch allocation at the top of
+ * frangi3d (frangi.cpp:158-163).  beta_one/beta_two are 2-D only and unused.
+ * The volume is split into ndev contiguous z-slabs, one per device; halos of
+ * the xy-smoothed volume are exchanged between neighbouring slabs per scale.
+ * device_ids == NULL means devices 0..ndev-1.  `sigmas` must be ascending as
+ * the caller guarantees (Advantra_plugin.cpp:1895). */
+int frangi_gpu_create(frangi_gpu_t** out, const float* sigmas, int nsig, float zdist,
+                      float alpha, float beta, float C, int blackwhite,
+                      int w, int h, int l, const int* device_ids, int ndev, unsigned flags);
+
+/* ---- one-slab handle for one-process-per-GPU jobs (torchrun) --------------
+ * This rank owns planes [z_begin, z_end) of the w*h*l volume and talks to ranks
+ * rank-1 / rank+1 over NCCL send/recv.  nccl_unique_id is the 128-byte id from
+ * frangi_gpu_nccl_unique_id on rank 0, distributed by the caller (ignored when
+ * nranks == 1).  All host/device buffers passed to run calls on this handle
+ * cover only the rank's own planes. */
+int frangi_gpu_create_slab(frangi_gpu_t** out, const float* sigmas, int nsig, float zdist,
+                           float alpha, float beta, float C, int blackwhite,
+                           int w, int h, int l, int z_begin, int z_end,
+                           int rank, int nranks, const void* nccl_unique_id,
+                           int device, unsigned flags);
+
+int frangi_gpu_nccl_unique_id(void* out128);
+
+/* Replaces: Frangi::~Frangi and the delete[]s at frangi.cpp:279-284. */
+void frangi_gpu_destroy(frangi_gpu_t* h);
+
+/* ---- the hot call ----------------------------------------------------------
+ * Replaces: void Frangi::frangi3d(unsigned char* I, int w, int h, int l,
+ *     float* J, float& Jmin, float& Jmax, unsigned char* Vx, Vy, Vz)
+ * (frangi.h:33, frangi.cpp:152-289).  Host buffers; copies are inside the call.
+ * J_host may be NULL when only J8_host is wanted (the caller at
+ * Advantra_plugin.cpp:2499-2514 converts J to 8 bits and frees J at once);
+ * J8_host, scale_idx_host, dir_xyz_host are optional (NULL) extras:
+ *   J8        = clamp(round((J-Jmin)/(Jmax-Jmin)*255)), 0 when |Jmax-Jmin|<=FLT_MIN
+ *   scale_idx = index into sigmas[] of the scale that produced J
+ *   dir_xyz   = 3 planar float32 volumes (all x, then all y, then all z). */
+int frangi_gpu_run(frangi_gpu_t* h, const uint8_t* I_host,
+                   float* J_host, float* Jmin, float* Jmax,
+                   uint8_t* Vx_host, uint8_t* Vy_host, uint8_t* Vz_host,
+                   uint8_t* J8_host, uint8_t* scale_idx_host, float* dir_xyz_host);
+
+/* Device-resident variant (single-device handles only): I_dev is a dense uint8
+ * device buffer of the handle's planes; results stay on the device and are read
+ * through frangi_gpu_device_outputs.  Asynchronous on the handle's stream;
+ * frangi_gpu_sync waits.  Used for kernel-only timing. */
+int frangi_gpu_run_device(frangi_gpu_t* h, const uint8_t* I_dev, float* Jmin, float* Jmax);
+int frangi_gpu_upload(frangi_gpu_t* h, const uint8_t* I_host); /* fills the handle's own input buffer */
+int frangi_gpu_run_resident(frangi_gpu_t* h, float* Jmin, float* Jmax); /* runs on that buffer */
+int frangi_gpu_sync(frangi_gpu_t* h);
+
+typedef struct frangi_gpu_outputs {
+    const float* J;          /* device pointers, dense, own planes */
+    const uint8_t* Vx;
+    const uint8_t* Vy;
+    const uint8_t* Vz;
+    const uint8_t* scale_idx; /* NULL unless FRANGI_GPU_FLAG_SCALE_IDX */
+    const float* dir_xyz;     /* NULL unless FRANGI_GPU_FLAG_DIR_F32 */
+    int64_t voxels;           /* own voxels = w*h*(z_end-z_begin) */
+} frangi_gpu_outputs_t;
+int frangi_gpu_device_outputs(frangi_gpu_t* h, int slab, frangi_gpu_outputs_t* out);
+
+/* Copies results of the last run to host buffers (any may be NULL). */
+int frangi_gpu_download(frangi_gpu_t* h, float* J_host, uint8_t* Vx_host, uint8_t* Vy_host,
+                        uint8_t* Vz_host, uint8_t* J8_host, uint8_t* scale_idx_host,
+                        float* dir_xyz_host);
+
+/* ---- stage entry points (parity tests, and the other public Frangi members) --
+ * Replaces: static Frangi::imgaussian(I,w,h,l,sig,zdist,F) (frangi.h:42,
+ * frangi.cpp:647-784) and Frangi::hessian3d (frangi.h:35, frangi.cpp:291-390).
+ * Host buffers, device 0 of the handle-less call. */
+int frangi_gpu_imgaussian(const uint8_t* I_host, int w, int h, int l, float sigma, float zdist,
+                          float* F_host, int device, unsigned flags);
+int frangi_gpu_hessian3d(const uint8_t* I_host, int w, int h, int l, float sigma, float zdist,
+                         float* Dzz, float* Dyy, float* Dyz, float* Dxx, float* Dxy, float* Dxz,
+                         int device, unsigned flags);
+/* Per-voxel stage alone: eigen-decomposition + vesselness + direction of n
+ * symmetric 3x3 matrices given as six float32 arrays (host).  v_out[n],
+ * dir_out[3*n] planar, lambda_out[3*n] interleaved |l1|<=|l2|<=|l3| (nullable). */
+int frangi_gpu_vesselness_stage(const float* Dxx, const float* Dxy, const float* Dxz,
+                                const float* Dyy, const float* Dyz, const float* Dzz, int64_t n,
+                                float alpha, float beta, float C, int blackwhite,
+                                float* v_out, float* dir_out, float* lambda_out, int device);
+
+/* ---- utilities --------------------------------------------------------------*/
+void* frangi_gpu_host_alloc(size_t bytes); /* pinned host memory (NULL on failure) */
+void frangi_gpu_host_free(void* p);
+int frangi_gpu_device_count(void);
+/* kernels launched by this library in this process so far */
+uint64_t frangi_gpu_launch_count(void);
+/* per-kernel-class device time of the last run on slab 0, milliseconds:
+ * [0]=gauss_xy [1]=gauss_z [2]=hessian_eigen [3]=minmax/j8 [4]=halo wait; n<=8 */
+int frangi_gpu_last_timings(frangi_gpu_t* h, float* ms, int n);
+const char* frangi_gpu_last_error(void);
+const char* frangi_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRANGI_GPU_H */

@@ -1,0 +1,9 @@
+"""pnr_b200 -- B200-native multi-scale 3-D Frangi filter (the hot path of
+miroslavradojevic/pnr's Advantra plugin) behind the reference's Frangi class
+interface.  CUDA kernels + C-ABI live in csrc/ (built into _lib/); this package
+is the thin Python host mirror used by tests and benchmarks."""
+from .frangi import (FLAG_DIR_F32, FLAG_FMA_SMOOTHING, FLAG_SCALE_IDX, Frangi, FrangiGpuError,
+                     FrangiPlan, PinnedBuffer, launch_count, load_library)
+
+__all__ = ["Frangi", "FrangiPlan", "FrangiGpuError", "PinnedBuffer", "load_library", "launch_count",
+           "FLAG_FMA_SMOOTHING", "FLAG_DIR_F32", "FLAG_SCALE_IDX"]

@@ -1,0 +1,866 @@
+// frangi_gpu.cu -- host side of the C-ABI declared in include/frangi_gpu.h.
+//
+// Owns device memory, streams, events and NCCL communicators; plans the tap
+// tables exactly as the reference does on the host (frangi.cpp:651-680) and
+// launches the kernels of frangi_kernels.cuh.  One `Slab` per device; a handle
+// holds one slab (one-process-per-GPU jobs) or several (one process driving a
+// whole box).  Per scale: xy smoothing of the slab's boundary planes, halo
+// exchange of those planes with the z neighbours (NCCL send/recv on a side
+// stream) overlapped with the xy smoothing of the interior, then the z pass and
+// the fused Hessian/eigen/vesselness/max kernel.
+#include "../../include/frangi_gpu.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "frangi_kernels.cuh"
+#include "nccl_dyn.h"
+
+#define FRANGI_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+using namespace frangi;
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(expr)                                                                         \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? FRANGI_GPU_ENOMEM : FRANGI_GPU_ECUDA, \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define NK(expr)                                                                         \
+    do {                                                                                 \
+        ncclx::ncclResult_t _r = (expr);                                                 \
+        if (_r != ncclx::ncclSuccess)                                                    \
+            return fail(FRANGI_GPU_ENCCL, "%s failed: %s (%s:%d)", #expr,                \
+                        ncclx::api().GetErrorString ? ncclx::api().GetErrorString(_r) : "?", \
+                        __FILE__, __LINE__);                                             \
+    } while (0)
+
+#define RC(expr)                      \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc) return _rc;          \
+    } while (0)
+
+// ---- tap planning (host; mirrors frangi.cpp:651-680 in float32) -------------
+constexpr int kRadii[] = { 3, 6, 9, 12, 15, 18, 24, 30 };
+constexpr int kNumRadii = sizeof(kRadii) / sizeof(kRadii[0]);
+
+int reference_radius(float sigma) { return (int)std::ceil(3 * sigma); }
+
+// Taps of true radius r are centred in a table of template radius R >= r and
+// padded with zeros: acc + v*0 leaves acc untouched bit for bit, so a kernel
+// instantiated for R reproduces the radius-r filter exactly.
+int plan_taps(float sigma, int& r_true, int& r_tmpl, GaussTaps& t)
+{
+    r_true = reference_radius(sigma);
+    r_tmpl = -1;
+    for (int i = 0; i < kNumRadii; ++i)
+        if (kRadii[i] >= r_true) { r_tmpl = kRadii[i]; break; }
+    if (r_tmpl < 0 || r_true < 0)
+        return fail(FRANGI_GPU_EINVAL, "sigma %g needs tap radius %d > supported %d", sigma, r_true, kMaxRadius);
+    std::vector<float> g(2 * r_true + 1);
+    float norm = 0;
+    for (int i = -r_true; i <= r_true; ++i) {
+        g[i + r_true] = std::exp(-(i * i) / (2 * sigma * sigma));  // float exp, as the reference
+        norm += g[i + r_true];
+    }
+    for (auto& v : g) v /= norm;
+    std::memset(&t, 0, sizeof t);
+    for (int i = -r_true; i <= r_true; ++i) t.g[i + r_tmpl] = g[i + r_true];
+    return 0;
+}
+
+struct ScalePlan {
+    float sigma, sigma2;
+    int rxy, rxy_t, rz, rz_t;
+    GaussTaps txy, tz;
+};
+
+// ---- kernel dispatch ----------------------------------------------------------
+template <int L, bool EXACT>
+int launch_xy_t(const XYParams& p, const GaussTaps& t, int nblocks, cudaStream_t s)
+{
+    using C = XYCfg<L>;
+    auto k = gauss_xy_kernel<L, EXACT>;
+    static thread_local int configured_dev[64] = { 0 };
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 64 && !configured_dev[dev]) {
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured_dev[dev] = 1;
+    }
+    k<<<nblocks, C::NT, C::SMEM_BYTES, s>>>(p, t);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <bool EXACT>
+int launch_xy_e(int L, const XYParams& p, const GaussTaps& t, int nblocks, cudaStream_t s)
+{
+    switch (L) {
+        case 3: return launch_xy_t<3, EXACT>(p, t, nblocks, s);
+        case 6: return launch_xy_t<6, EXACT>(p, t, nblocks, s);
+        case 9: return launch_xy_t<9, EXACT>(p, t, nblocks, s);
+        case 12: return launch_xy_t<12, EXACT>(p, t, nblocks, s);
+        case 15: return launch_xy_t<15, EXACT>(p, t, nblocks, s);
+        case 18: return launch_xy_t<18, EXACT>(p, t, nblocks, s);
+        case 24: return launch_xy_t<24, EXACT>(p, t, nblocks, s);
+        case 30: return launch_xy_t<30, EXACT>(p, t, nblocks, s);
+    }
+    return fail(FRANGI_GPU_EINVAL, "no gauss_xy instantiation for radius %d", L);
+}
+
+template <int L, bool EXACT>
+int launch_z_t(const ZParams& p, const GaussTaps& t, long long nblocks, cudaStream_t s)
+{
+    gauss_z_kernel<L, EXACT><<<(unsigned)nblocks, 128, 0, s>>>(p, t);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <bool EXACT>
+int launch_z_e(int L, const ZParams& p, const GaussTaps& t, long long nblocks, cudaStream_t s)
+{
+    switch (L) {
+        case 3: return launch_z_t<3, EXACT>(p, t, nblocks, s);
+        case 6: return launch_z_t<6, EXACT>(p, t, nblocks, s);
+        case 9: return launch_z_t<9, EXACT>(p, t, nblocks, s);
+        case 12: return launch_z_t<12, EXACT>(p, t, nblocks, s);
+        case 15: return launch_z_t<15, EXACT>(p, t, nblocks, s);
+        case 18: return launch_z_t<18, EXACT>(p, t, nblocks, s);
+        case 24: return launch_z_t<24, EXACT>(p, t, nblocks, s);
+        case 30: return launch_z_t<30, EXACT>(p, t, nblocks, s);
+    }
+    return fail(FRANGI_GPU_EINVAL, "no gauss_z instantiation for radius %d", L);
+}
+
+// ---- one z-slab on one device -----------------------------------------------
+struct Slab {
+    int dev = 0;
+    int index = 0;            // position of the slab in the volume (global rank)
+    int zb = 0, ze = 0;       // own planes
+    int fb = 0, fe = 0;       // planes of F held: own +-2, clipped to the volume
+    int xb = 0, xe = 0;       // planes of Fxy held: F planes +- max z radius, clipped
+    long long voxels = 0;     // own voxels
+    uint8_t* dI = nullptr;
+    float* dFxy = nullptr;
+    float* dF = nullptr;
+    float* dJ = nullptr;
+    uint8_t *dVx = nullptr, *dVy = nullptr, *dVz = nullptr, *dScale = nullptr, *dJ8 = nullptr;
+    float* dDir = nullptr;
+    int* dMinMax = nullptr;
+    int* hMinMax = nullptr;   // pinned
+    cudaStream_t s_main = nullptr, s_comm = nullptr;
+    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
+    std::vector<cudaEvent_t> ev_time;   // 4 per scale + 2
+    ncclx::ncclComm_t comm = nullptr;
+};
+
+}  // namespace
+
+struct frangi_gpu {
+    int w = 0, h = 0, l = 0;
+    int fpitch = 0;
+    long long fplane = 0;
+    float zdist = 1, alpha = .5f, beta = .5f, C = 500;
+    int blackwhite = 0;
+    unsigned flags = 0;
+    int nslabs_total = 1;        // slabs in the whole job (all processes)
+    int rz_max = 0;
+    std::vector<ScalePlan> scales;
+    std::vector<Slab> slabs;     // slabs driven by this process
+    bool ran = false;
+    float last_ms[8] = { 0 };
+};
+
+namespace {
+
+void free_slab(Slab& s)
+{
+    cudaSetDevice(s.dev);
+    if (s.comm && ncclx::api().ok) ncclx::api().CommDestroy(s.comm);
+    cudaFree(s.dI); cudaFree(s.dFxy); cudaFree(s.dF); cudaFree(s.dJ);
+    cudaFree(s.dVx); cudaFree(s.dVy); cudaFree(s.dVz); cudaFree(s.dScale); cudaFree(s.dJ8);
+    cudaFree(s.dDir); cudaFree(s.dMinMax);
+    if (s.hMinMax) cudaFreeHost(s.hMinMax);
+    for (auto e : s.ev_time) cudaEventDestroy(e);
+    if (s.ev_boundary) cudaEventDestroy(s.ev_boundary);
+    if (s.ev_halo) cudaEventDestroy(s.ev_halo);
+    if (s.s_main) cudaStreamDestroy(s.s_main);
+    if (s.s_comm) cudaStreamDestroy(s.s_comm);
+    s = Slab();
+}
+
+int check_device(int dev)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(FRANGI_GPU_ECUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (dev < 0 || dev >= n) return fail(FRANGI_GPU_EINVAL, "device %d out of range (0..%d)", dev, n - 1);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(FRANGI_GPU_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                    prop.major, prop.minor);
+    return 0;
+}
+
+int plan_common(frangi_gpu* H, const float* sigmas, int nsig, float zdist, float alpha, float beta,
+                float C, int blackwhite, int w, int h, int l, unsigned flags)
+{
+    if (!sigmas || nsig < 1 || nsig > 64) return fail(FRANGI_GPU_EINVAL, "nsig must be 1..64");
+    if (w < 2 || h < 2 || l < 2)
+        return fail(FRANGI_GPU_EINVAL, "frangi3d needs w,h,l >= 2 (got %d,%d,%d); 2-D images are out of scope", w, h, l);
+    if (h > 65535) return fail(FRANGI_GPU_EINVAL, "h > 65535 not supported");
+    if (!(zdist > 0)) return fail(FRANGI_GPU_EINVAL, "zdist must be > 0");
+    H->w = w; H->h = h; H->l = l;
+    H->fpitch = (w + 31) / 32 * 32;
+    H->fplane = (long long)H->fpitch * h;
+    H->zdist = zdist; H->alpha = alpha; H->beta = beta; H->C = C;
+    H->blackwhite = blackwhite; H->flags = flags;
+    H->scales.resize(nsig);
+    H->rz_max = 0;
+    for (int i = 0; i < nsig; ++i) {
+        ScalePlan& sp = H->scales[i];
+        if (!(sigmas[i] > 0)) return fail(FRANGI_GPU_EINVAL, "sigma[%d] must be > 0", i);
+        sp.sigma = sigmas[i];
+        sp.sigma2 = sigmas[i] * sigmas[i];
+        RC(plan_taps(sp.sigma, sp.rxy, sp.rxy_t, sp.txy));
+        const float sigma_z = sp.sigma / zdist;   // frangi.cpp:649
+        RC(plan_taps(sigma_z, sp.rz, sp.rz_t, sp.tz));
+        if (sp.rz > H->rz_max) H->rz_max = sp.rz;
+    }
+    return 0;
+}
+
+int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
+{
+    s.dev = dev; s.index = index; s.zb = zb; s.ze = ze;
+    s.fb = std::max(zb - 2, 0);
+    s.fe = std::min(ze + 2, H->l);
+    s.xb = std::max(s.fb - H->rz_max, 0);
+    s.xe = std::min(s.fe + H->rz_max, H->l);
+    s.voxels = (long long)H->w * H->h * (ze - zb);
+    CK(cudaSetDevice(dev));
+    CK(cudaStreamCreateWithFlags(&s.s_main, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s.ev_boundary, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_halo, cudaEventDisableTiming));
+    s.ev_time.resize(4 * H->scales.size() + 2);
+    for (auto& e : s.ev_time) CK(cudaEventCreate(&e));
+    CK(cudaMalloc(&s.dI, (size_t)s.voxels));
+    CK(cudaMalloc(&s.dFxy, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
+    CK(cudaMalloc(&s.dF, sizeof(float) * (size_t)H->fplane * (s.fe - s.fb)));
+    CK(cudaMalloc(&s.dJ, sizeof(float) * (size_t)s.voxels));
+    CK(cudaMalloc(&s.dVx, (size_t)s.voxels));
+    CK(cudaMalloc(&s.dVy, (size_t)s.voxels));
+    CK(cudaMalloc(&s.dVz, (size_t)s.voxels));
+    CK(cudaMalloc(&s.dJ8, (size_t)s.voxels));
+    if (H->flags & FRANGI_GPU_FLAG_SCALE_IDX) CK(cudaMalloc(&s.dScale, (size_t)s.voxels));
+    if (H->flags & FRANGI_GPU_FLAG_DIR_F32) CK(cudaMalloc(&s.dDir, sizeof(float) * 3 * (size_t)s.voxels));
+    CK(cudaMalloc(&s.dMinMax, 2 * sizeof(int)));
+    CK(cudaHostAlloc(&s.hMinMax, 2 * sizeof(int), cudaHostAllocDefault));
+    return 0;
+}
+
+// xy smoothing of own planes [z0, z1) of slab s for one scale
+int launch_xy(frangi_gpu* H, Slab& s, const ScalePlan& sp, const uint8_t* I_own, int z0, int z1)
+{
+    if (z1 <= z0) return 0;
+    XYParams p;
+    p.I = I_own + (long long)(z0 - s.zb) * H->w * H->h;
+    p.out = s.dFxy + (long long)(z0 - s.xb) * H->fplane;
+    p.w = H->w; p.h = H->h; p.nz = z1 - z0;
+    p.fpitch = H->fpitch; p.fplane = H->fplane;
+    p.nstrips = (H->w + 255) / 256;
+    // enough CTAs to fill 148 SMs a few times over, else split y into segments
+    const long long want = 148 * 4;
+    const long long per_seg = (long long)p.nstrips * p.nz;
+    int nsegs = (int)std::min<long long>((want + per_seg - 1) / per_seg, (H->h + 31) / 32);
+    if (nsegs < 1) nsegs = 1;
+    int seg_h = ((H->h + nsegs - 1) / nsegs + 15) / 16 * 16;
+    p.seg_h = seg_h;
+    p.nsegs = (H->h + seg_h - 1) / seg_h;
+    p.vec_ok = (H->w % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.I) & 3) == 0);
+    const long long nblocks = (long long)p.nstrips * p.nsegs * p.nz;
+    if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+    if (H->flags & FRANGI_GPU_FLAG_FMA_SMOOTHING)
+        return launch_xy_e<false>(sp.rxy_t, p, sp.txy, (int)nblocks, s.s_main);
+    return launch_xy_e<true>(sp.rxy_t, p, sp.txy, (int)nblocks, s.s_main);
+}
+
+int launch_z(frangi_gpu* H, Slab& s, const ScalePlan& sp)
+{
+    ZParams p;
+    p.in = s.dFxy; p.out = s.dF;
+    p.w = H->w; p.h = H->h; p.l = H->l;
+    p.fpitch = H->fpitch; p.fplane = H->fplane;
+    p.in_base = s.xb; p.in_count = s.xe - s.xb;
+    p.out_base = s.fb; p.out_count = s.fe - s.fb;
+    p.nzc = (p.out_count + 7) / 8;
+    p.nxs = (H->w + 127) / 128;
+    const long long nblocks = (long long)p.nzc * p.nxs * H->h;
+    if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+    if (H->flags & FRANGI_GPU_FLAG_FMA_SMOOTHING) return launch_z_e<false>(sp.rz_t, p, sp.tz, nblocks, s.s_main);
+    return launch_z_e<true>(sp.rz_t, p, sp.tz, nblocks, s.s_main);
+}
+
+FView make_fview(frangi_gpu* H, Slab& s)
+{
+    FView f;
+    f.F = s.dF; f.w = H->w; f.h = H->h; f.l = H->l;
+    f.fpitch = H->fpitch; f.fplane = H->fplane; f.base = s.fb;
+    return f;
+}
+
+FrangiConsts make_consts(frangi_gpu* H, float sigma2)
+{
+    FrangiConsts k;
+    const float a2 = 2 * H->alpha * H->alpha, b2 = 2 * H->beta * H->beta, c2 = 2 * H->C * H->C;
+    k.inv_2a2 = 1.0f / a2; k.inv_2b2 = 1.0f / b2; k.inv_2c2 = 1.0f / c2;
+    k.sigma2 = sigma2; k.blackwhite = H->blackwhite;
+    return k;
+}
+
+int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si)
+{
+    VoxelParams p;
+    p.f = make_fview(H, s);
+    p.J = s.dJ; p.Vx = s.dVx; p.Vy = s.dVy; p.Vz = s.dVz;
+    p.scale_idx = s.dScale; p.dir = s.dDir; p.voxels = s.voxels;
+    p.z_begin = s.zb; p.nz = s.ze - s.zb;
+    p.scale = si; p.first_scale = si == 0; p.last_scale = si == (int)H->scales.size() - 1;
+    p.minmax = s.dMinMax;
+    p.k = make_consts(H, sp.sigma2);
+    dim3 grid((H->w + 127) / 128, H->h, s.ze - s.zb);
+    hessian_eigen_kernel<<<grid, 128, 0, s.s_main>>>(p);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Exchange the xy-smoothed boundary planes of every local slab with its z
+// neighbours.  Slab k sends its lowest `halo` own planes down and its highest
+// `halo` own planes up, and receives the matching planes into the halo regions
+// of its Fxy buffer.  All calls of all local slabs sit in one NCCL group.
+int exchange_halos(frangi_gpu* H, int halo)
+{
+    if (H->nslabs_total == 1) return 0;
+    auto& N = ncclx::api();
+    const size_t plane = (size_t)H->fplane;
+    NK(N.GroupStart());
+    for (auto& s : H->slabs) {
+        const bool has_lo = s.index > 0, has_hi = s.index < H->nslabs_total - 1;
+        if (has_lo) {
+            const int n_recv = s.zb - std::max(s.zb - halo, 0);
+            NK(N.Send(s.dFxy + (size_t)(s.zb - s.xb) * plane, (size_t)halo * plane, ncclx::ncclFloat32,
+                      s.index - 1, s.comm, s.s_comm));
+            NK(N.Recv(s.dFxy + (size_t)(s.zb - n_recv - s.xb) * plane, (size_t)n_recv * plane,
+                      ncclx::ncclFloat32, s.index - 1, s.comm, s.s_comm));
+        }
+        if (has_hi) {
+            const int n_recv = std::min(s.ze + halo, H->l) - s.ze;
+            NK(N.Send(s.dFxy + (size_t)(s.ze - halo - s.xb) * plane, (size_t)halo * plane, ncclx::ncclFloat32,
+                      s.index + 1, s.comm, s.s_comm));
+            NK(N.Recv(s.dFxy + (size_t)(s.ze - s.xb) * plane, (size_t)n_recv * plane, ncclx::ncclFloat32,
+                      s.index + 1, s.comm, s.s_comm));
+        }
+    }
+    NK(N.GroupEnd());
+    return 0;
+}
+
+// The whole multi-scale pipeline on inputs already resident on the devices.
+// I_own[k] = dense u8 planes of local slab k.
+int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
+{
+    const int S = (int)H->scales.size();
+    const bool multi = H->nslabs_total > 1;
+    for (size_t k = 0; k < H->slabs.size(); ++k) {
+        Slab& s = H->slabs[k];
+        CK(cudaSetDevice(s.dev));
+        s.hMinMax[0] = 0x7f7fffff;            // FLT_MAX  (frangi.cpp:176)
+        s.hMinMax[1] = (int)0xff7fffffu;      // -FLT_MAX (frangi.cpp:177)
+        CK(cudaMemcpyAsync(s.dMinMax, s.hMinMax, 2 * sizeof(int), cudaMemcpyHostToDevice, s.s_main));
+        CK(cudaEventRecord(s.ev_time[0], s.s_main));
+    }
+    for (int si = 0; si < S; ++si) {
+        const ScalePlan& sp = H->scales[si];
+        const int halo = sp.rz + 2;
+        if (multi) {
+            // boundary planes first, so that the exchange overlaps the interior
+            for (size_t k = 0; k < H->slabs.size(); ++k) {
+                Slab& s = H->slabs[k];
+                CK(cudaSetDevice(s.dev));
+                const int nz = s.ze - s.zb;
+                if (nz <= 2 * halo) {
+                    RC(launch_xy(H, s, sp, I_own[k], s.zb, s.ze));
+                } else {
+                    RC(launch_xy(H, s, sp, I_own[k], s.zb, s.zb + halo));
+                    RC(launch_xy(H, s, sp, I_own[k], s.ze - halo, s.ze));
+                }
+                CK(cudaEventRecord(s.ev_boundary, s.s_main));
+                CK(cudaStreamWaitEvent(s.s_comm, s.ev_boundary, 0));
+            }
+            RC(exchange_halos(H, halo));
+            for (size_t k = 0; k < H->slabs.size(); ++k) {
+                Slab& s = H->slabs[k];
+                CK(cudaSetDevice(s.dev));
+                CK(cudaEventRecord(s.ev_halo, s.s_comm));
+                const int nz = s.ze - s.zb;
+                if (nz > 2 * halo) RC(launch_xy(H, s, sp, I_own[k], s.zb + halo, s.ze - halo));
+                CK(cudaEventRecord(s.ev_time[1 + 4 * si], s.s_main));
+                CK(cudaStreamWaitEvent(s.s_main, s.ev_halo, 0));
+                CK(cudaEventRecord(s.ev_time[2 + 4 * si], s.s_main));
+            }
+        } else {
+            Slab& s = H->slabs[0];
+            CK(cudaSetDevice(s.dev));
+            RC(launch_xy(H, s, sp, I_own[0], s.zb, s.ze));
+            CK(cudaEventRecord(s.ev_time[1 + 4 * si], s.s_main));
+            CK(cudaEventRecord(s.ev_time[2 + 4 * si], s.s_main));
+        }
+        for (size_t k = 0; k < H->slabs.size(); ++k) {
+            Slab& s = H->slabs[k];
+            CK(cudaSetDevice(s.dev));
+            RC(launch_z(H, s, sp));
+            CK(cudaEventRecord(s.ev_time[3 + 4 * si], s.s_main));
+            RC(launch_voxel(H, s, sp, si));
+            CK(cudaEventRecord(s.ev_time[4 + 4 * si], s.s_main));
+        }
+    }
+    // global Jmin / Jmax across slabs, then the 8-bit normalisation
+    if (multi) {
+        auto& N = ncclx::api();
+        NK(N.GroupStart());
+        for (auto& s : H->slabs) {
+            NK(N.AllReduce(s.dMinMax, s.dMinMax, 1, ncclx::ncclInt32, ncclx::ncclMin, s.comm, s.s_main));
+            NK(N.AllReduce(s.dMinMax + 1, s.dMinMax + 1, 1, ncclx::ncclInt32, ncclx::ncclMax, s.comm, s.s_main));
+        }
+        NK(N.GroupEnd());
+    }
+    for (auto& s : H->slabs) {
+        CK(cudaSetDevice(s.dev));
+        const int nb = (int)std::min<long long>((s.voxels + 255) / 256, 148 * 16);
+        j_to_j8_kernel<<<nb, 256, 0, s.s_main>>>(s.dJ, s.dJ8, s.voxels, s.dMinMax);
+        g_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(s.hMinMax, s.dMinMax, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.s_main));
+        CK(cudaEventRecord(s.ev_time[4 * S + 1], s.s_main));
+    }
+    H->ran = true;
+    return 0;
+}
+
+int sync_all(frangi_gpu* H)
+{
+    for (auto& s : H->slabs) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.s_main));
+        CK(cudaStreamSynchronize(s.s_comm));
+    }
+    return 0;
+}
+
+int collect(frangi_gpu* H, float* Jmin, float* Jmax)
+{
+    RC(sync_all(H));
+    Slab& s0 = H->slabs[0];
+    float lo, hi;
+    std::memcpy(&lo, &s0.hMinMax[0], 4);
+    std::memcpy(&hi, &s0.hMinMax[1], 4);
+    if (Jmin) *Jmin = lo;
+    if (Jmax) *Jmax = hi;
+    // per-class device times of slab 0
+    const int S = (int)H->scales.size();
+    std::memset(H->last_ms, 0, sizeof H->last_ms);
+    CK(cudaSetDevice(s0.dev));
+    for (int si = 0; si < S; ++si) {
+        float t;
+        cudaEvent_t prev = si == 0 ? s0.ev_time[0] : s0.ev_time[4 * si];
+        CK(cudaEventElapsedTime(&t, prev, s0.ev_time[1 + 4 * si])); H->last_ms[0] += t;
+        CK(cudaEventElapsedTime(&t, s0.ev_time[1 + 4 * si], s0.ev_time[2 + 4 * si])); H->last_ms[4] += t;
+        CK(cudaEventElapsedTime(&t, s0.ev_time[2 + 4 * si], s0.ev_time[3 + 4 * si])); H->last_ms[1] += t;
+        CK(cudaEventElapsedTime(&t, s0.ev_time[3 + 4 * si], s0.ev_time[4 + 4 * si])); H->last_ms[2] += t;
+    }
+    float t;
+    CK(cudaEventElapsedTime(&t, s0.ev_time[4 * S], s0.ev_time[4 * S + 1])); H->last_ms[3] = t;
+    CK(cudaEventElapsedTime(&t, s0.ev_time[0], s0.ev_time[4 * S + 1])); H->last_ms[5] = t;
+    return 0;
+}
+
+int download_slab(frangi_gpu* H, Slab& s, long long off, float* J, uint8_t* Vx, uint8_t* Vy, uint8_t* Vz,
+                  uint8_t* J8, uint8_t* sc, float* dir, long long total_voxels)
+{
+    CK(cudaSetDevice(s.dev));
+    const size_t n = (size_t)s.voxels;
+    if (J) CK(cudaMemcpyAsync(J + off, s.dJ, n * 4, cudaMemcpyDeviceToHost, s.s_main));
+    if (Vx) CK(cudaMemcpyAsync(Vx + off, s.dVx, n, cudaMemcpyDeviceToHost, s.s_main));
+    if (Vy) CK(cudaMemcpyAsync(Vy + off, s.dVy, n, cudaMemcpyDeviceToHost, s.s_main));
+    if (Vz) CK(cudaMemcpyAsync(Vz + off, s.dVz, n, cudaMemcpyDeviceToHost, s.s_main));
+    if (J8) CK(cudaMemcpyAsync(J8 + off, s.dJ8, n, cudaMemcpyDeviceToHost, s.s_main));
+    if (sc) {
+        if (!s.dScale) return fail(FRANGI_GPU_ESTATE, "scale index not kept: create with FRANGI_GPU_FLAG_SCALE_IDX");
+        CK(cudaMemcpyAsync(sc + off, s.dScale, n, cudaMemcpyDeviceToHost, s.s_main));
+    }
+    if (dir) {
+        if (!s.dDir) return fail(FRANGI_GPU_ESTATE, "float direction not kept: create with FRANGI_GPU_FLAG_DIR_F32");
+        for (int c = 0; c < 3; ++c)
+            CK(cudaMemcpyAsync(dir + (size_t)c * total_voxels + off, s.dDir + (size_t)c * n, n * 4,
+                               cudaMemcpyDeviceToHost, s.s_main));
+    }
+    return 0;
+}
+
+long long local_voxels(frangi_gpu* H)
+{
+    long long n = 0;
+    for (auto& s : H->slabs) n += s.voxels;
+    return n;
+}
+
+}  // namespace
+
+// =============================== C-ABI ========================================
+
+FRANGI_API const char* frangi_gpu_last_error(void) { return g_err.c_str(); }
+FRANGI_API const char* frangi_gpu_version(void) { return "frangi-b200 0.1 (sm_100a)"; }
+FRANGI_API uint64_t frangi_gpu_launch_count(void) { return g_launches.load(); }
+
+FRANGI_API int frangi_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+FRANGI_API void* frangi_gpu_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail(FRANGI_GPU_ENOMEM, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+FRANGI_API void frangi_gpu_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+FRANGI_API int frangi_gpu_nccl_unique_id(void* out128)
+{
+    auto& N = ncclx::api();
+    if (!N.ok) return fail(FRANGI_GPU_ENCCL, "libnccl.so.2 not found or incomplete");
+    ncclx::ncclUniqueId id;
+    NK(N.GetUniqueId(&id));
+    std::memcpy(out128, &id, 128);
+    return 0;
+}
+
+FRANGI_API void frangi_gpu_destroy(frangi_gpu_t* H)
+{
+    if (!H) return;
+    for (auto& s : H->slabs) free_slab(s);
+    delete H;
+}
+
+FRANGI_API int frangi_gpu_create(frangi_gpu_t** out, const float* sigmas, int nsig, float zdist, float alpha,
+                                 float beta, float C, int blackwhite, int w, int h, int l,
+                                 const int* device_ids, int ndev, unsigned flags)
+{
+    if (!out) return fail(FRANGI_GPU_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (ndev < 1) return fail(FRANGI_GPU_EINVAL, "ndev must be >= 1");
+    frangi_gpu* H = new (std::nothrow) frangi_gpu();
+    if (!H) return fail(FRANGI_GPU_ENOMEM, "out of host memory");
+    int rc = plan_common(H, sigmas, nsig, zdist, alpha, beta, C, blackwhite, w, h, l, flags);
+    if (rc) { delete H; return rc; }
+    // a neighbour must be able to supply a whole halo: slab thickness >= rz_max + 2
+    const int min_thick = H->rz_max + 2;
+    int nuse = std::min(ndev, std::max(1, l / min_thick));
+    H->nslabs_total = nuse;
+    H->slabs.resize(nuse);
+    std::vector<int> devs(nuse);
+    for (int k = 0; k < nuse; ++k) devs[k] = device_ids ? device_ids[k] : k;
+    for (int k = 0; k < nuse && !rc; ++k) {
+        rc = check_device(devs[k]);
+        if (!rc) {
+            const int zb = (int)((long long)l * k / nuse), ze = (int)((long long)l * (k + 1) / nuse);
+            rc = alloc_slab(H, H->slabs[k], devs[k], k, zb, ze);
+        }
+    }
+    if (!rc && nuse > 1) {
+        auto& N = ncclx::api();
+        if (!N.ok) rc = fail(FRANGI_GPU_ENCCL, "libnccl.so.2 not found or incomplete");
+        else {
+            std::vector<ncclx::ncclComm_t> comms(nuse);
+            ncclx::ncclResult_t r = N.CommInitAll(comms.data(), nuse, devs.data());
+            if (r != ncclx::ncclSuccess) rc = fail(FRANGI_GPU_ENCCL, "ncclCommInitAll failed (%d)", (int)r);
+            else for (int k = 0; k < nuse; ++k) H->slabs[k].comm = comms[k];
+        }
+    }
+    if (rc) { frangi_gpu_destroy(H); return rc; }
+    *out = H;
+    return 0;
+}
+
+FRANGI_API int frangi_gpu_create_slab(frangi_gpu_t** out, const float* sigmas, int nsig, float zdist, float alpha,
+                                      float beta, float C, int blackwhite, int w, int h, int l, int z_begin,
+                                      int z_end, int rank, int nranks, const void* nccl_unique_id, int device,
+                                      unsigned flags)
+{
+    if (!out) return fail(FRANGI_GPU_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(FRANGI_GPU_EINVAL, "bad rank/nranks");
+    if (z_begin < 0 || z_end > l || z_end <= z_begin) return fail(FRANGI_GPU_EINVAL, "bad z range");
+    if ((rank == 0) != (z_begin == 0) || (rank == nranks - 1) != (z_end == l))
+        return fail(FRANGI_GPU_EINVAL, "slabs must tile [0,l) in rank order");
+    frangi_gpu* H = new (std::nothrow) frangi_gpu();
+    if (!H) return fail(FRANGI_GPU_ENOMEM, "out of host memory");
+    int rc = plan_common(H, sigmas, nsig, zdist, alpha, beta, C, blackwhite, w, h, l, flags);
+    if (!rc && nranks > 1 && (z_end - z_begin) < H->rz_max + 2)
+        rc = fail(FRANGI_GPU_EINVAL, "slab of %d planes is thinner than the halo %d", z_end - z_begin, H->rz_max + 2);
+    if (!rc) rc = check_device(device);
+    if (!rc) {
+        H->nslabs_total = nranks;
+        H->slabs.resize(1);
+        rc = alloc_slab(H, H->slabs[0], device, rank, z_begin, z_end);
+    }
+    if (!rc && nranks > 1) {
+        auto& N = ncclx::api();
+        if (!N.ok) rc = fail(FRANGI_GPU_ENCCL, "libnccl.so.2 not found or incomplete");
+        else if (!nccl_unique_id) rc = fail(FRANGI_GPU_EINVAL, "nccl_unique_id is NULL");
+        else {
+            ncclx::ncclUniqueId id;
+            std::memcpy(&id, nccl_unique_id, 128);
+            ncclx::ncclResult_t r = N.CommInitRank(&H->slabs[0].comm, nranks, id, rank);
+            if (r != ncclx::ncclSuccess) rc = fail(FRANGI_GPU_ENCCL, "ncclCommInitRank failed (%d)", (int)r);
+        }
+    }
+    if (rc) { frangi_gpu_destroy(H); return rc; }
+    *out = H;
+    return 0;
+}
+
+FRANGI_API int frangi_gpu_upload(frangi_gpu_t* H, const uint8_t* I_host)
+{
+    if (!H || !I_host) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    long long off = 0;
+    for (auto& s : H->slabs) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaMemcpyAsync(s.dI, I_host + off, (size_t)s.voxels, cudaMemcpyHostToDevice, s.s_main));
+        off += s.voxels;
+    }
+    return 0;
+}
+
+FRANGI_API int frangi_gpu_run_resident(frangi_gpu_t* H, float* Jmin, float* Jmax)
+{
+    if (!H) return fail(FRANGI_GPU_EINVAL, "NULL handle");
+    std::vector<const uint8_t*> in;
+    for (auto& s : H->slabs) in.push_back(s.dI);
+    RC(run_pipeline(H, in));
+    if (Jmin || Jmax) RC(collect(H, Jmin, Jmax));
+    return 0;
+}
+
+FRANGI_API int frangi_gpu_run_device(frangi_gpu_t* H, const uint8_t* I_dev, float* Jmin, float* Jmax)
+{
+    if (!H || !I_dev) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    if (H->slabs.size() != 1) return fail(FRANGI_GPU_ESTATE, "run_device needs a single-device handle");
+    std::vector<const uint8_t*> in(1, I_dev);
+    RC(run_pipeline(H, in));
+    if (Jmin || Jmax) RC(collect(H, Jmin, Jmax));
+    return 0;
+}
+
+FRANGI_API int frangi_gpu_sync(frangi_gpu_t* H)
+{
+    if (!H) return fail(FRANGI_GPU_EINVAL, "NULL handle");
+    return collect(H, nullptr, nullptr);
+}
+
+FRANGI_API int frangi_gpu_download(frangi_gpu_t* H, float* J, uint8_t* Vx, uint8_t* Vy, uint8_t* Vz, uint8_t* J8,
+                                   uint8_t* sc, float* dir)
+{
+    if (!H) return fail(FRANGI_GPU_EINVAL, "NULL handle");
+    if (!H->ran) return fail(FRANGI_GPU_ESTATE, "nothing has been run on this handle");
+    const long long total = local_voxels(H);
+    long long off = 0;
+    for (auto& s : H->slabs) {
+        RC(download_slab(H, s, off, J, Vx, Vy, Vz, J8, sc, dir, total));
+        off += s.voxels;
+    }
+    return sync_all(H);
+}
+
+FRANGI_API int frangi_gpu_run(frangi_gpu_t* H, const uint8_t* I_host, float* J, float* Jmin, float* Jmax,
+                              uint8_t* Vx, uint8_t* Vy, uint8_t* Vz, uint8_t* J8, uint8_t* sc, float* dir)
+{
+    if (!H || !I_host) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    RC(frangi_gpu_upload(H, I_host));
+    std::vector<const uint8_t*> in;
+    for (auto& s : H->slabs) in.push_back(s.dI);
+    RC(run_pipeline(H, in));
+    const long long total = local_voxels(H);
+    long long off = 0;
+    for (auto& s : H->slabs) {
+        RC(download_slab(H, s, off, J, Vx, Vy, Vz, J8, sc, dir, total));
+        off += s.voxels;
+    }
+    return collect(H, Jmin, Jmax);
+}
+
+FRANGI_API int frangi_gpu_device_outputs(frangi_gpu_t* H, int slab, frangi_gpu_outputs_t* out)
+{
+    if (!H || !out || slab < 0 || slab >= (int)H->slabs.size()) return fail(FRANGI_GPU_EINVAL, "bad argument");
+    Slab& s = H->slabs[slab];
+    out->J = s.dJ; out->Vx = s.dVx; out->Vy = s.dVy; out->Vz = s.dVz;
+    out->scale_idx = s.dScale; out->dir_xyz = s.dDir; out->voxels = s.voxels;
+    return 0;
+}
+
+FRANGI_API int frangi_gpu_last_timings(frangi_gpu_t* H, float* ms, int n)
+{
+    if (!H || !ms) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    for (int i = 0; i < n && i < 8; ++i) ms[i] = H->last_ms[i];
+    return 0;
+}
+
+// ---- stage entry points --------------------------------------------------------
+
+namespace {
+int stage_smooth(frangi_gpu_t** Hout, const uint8_t* I_host, int w, int h, int l, float sigma, float zdist,
+                 int device, unsigned flags)
+{
+    int dev = device;
+    RC(frangi_gpu_create(Hout, &sigma, 1, zdist, .5f, .5f, 500.f, 0, w, h, l, &dev, 1, flags));
+    frangi_gpu* H = *Hout;
+    Slab& s = H->slabs[0];
+    RC(frangi_gpu_upload(H, I_host));
+    RC(launch_xy(H, s, H->scales[0], s.dI, s.zb, s.ze));
+    RC(launch_z(H, s, H->scales[0]));
+    return 0;
+}
+}  // namespace
+
+FRANGI_API int frangi_gpu_imgaussian(const uint8_t* I_host, int w, int h, int l, float sigma, float zdist,
+                                     float* F_host, int device, unsigned flags)
+{
+    if (!I_host || !F_host) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    frangi_gpu* H = nullptr;
+    int rc = stage_smooth(&H, I_host, w, h, l, sigma, zdist, device, flags);
+    if (!rc) {
+        Slab& s = H->slabs[0];
+        cudaError_t e = cudaMemcpy2DAsync(F_host, (size_t)w * 4, s.dF, (size_t)H->fpitch * 4, (size_t)w * 4,
+                                          (size_t)h * l, cudaMemcpyDeviceToHost, s.s_main);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s.s_main);
+        if (e != cudaSuccess) rc = fail(FRANGI_GPU_ECUDA, "imgaussian copy-back: %s", cudaGetErrorString(e));
+    }
+    frangi_gpu_destroy(H);
+    return rc;
+}
+
+FRANGI_API int frangi_gpu_hessian3d(const uint8_t* I_host, int w, int h, int l, float sigma, float zdist,
+                                    float* Dzz, float* Dyy, float* Dyz, float* Dxx, float* Dxy, float* Dxz,
+                                    int device, unsigned flags)
+{
+    if (!I_host || !Dzz || !Dyy || !Dyz || !Dxx || !Dxy || !Dxz) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    frangi_gpu* H = nullptr;
+    int rc = stage_smooth(&H, I_host, w, h, l, sigma, zdist, device, flags);
+    float* host[6] = { Dzz, Dyy, Dyz, Dxx, Dxy, Dxz };
+    float* dD[6] = { nullptr };
+    if (!rc) {
+        Slab& s = H->slabs[0];
+        const size_t n = (size_t)s.voxels;
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < 6 && e == cudaSuccess; ++k) e = cudaMalloc(&dD[k], n * 4);
+        if (e == cudaSuccess) {
+            HessDumpParams p;
+            p.f = make_fview(H, s);
+            for (int k = 0; k < 6; ++k) p.D[k] = dD[k];
+            p.z_begin = 0; p.sigma2 = H->scales[0].sigma2;
+            dim3 grid((w + 127) / 128, h, l);
+            hessian_dump_kernel<<<grid, 128, 0, s.s_main>>>(p);
+            g_launches++;
+            e = cudaGetLastError();
+        }
+        for (int k = 0; k < 6 && e == cudaSuccess; ++k)
+            e = cudaMemcpyAsync(host[k], dD[k], n * 4, cudaMemcpyDeviceToHost, s.s_main);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s.s_main);
+        if (e != cudaSuccess) rc = fail(FRANGI_GPU_ECUDA, "hessian3d stage: %s", cudaGetErrorString(e));
+    }
+    for (int k = 0; k < 6; ++k) cudaFree(dD[k]);
+    frangi_gpu_destroy(H);
+    return rc;
+}
+
+FRANGI_API int frangi_gpu_vesselness_stage(const float* Dxx, const float* Dxy, const float* Dxz, const float* Dyy,
+                                           const float* Dyz, const float* Dzz, int64_t n, float alpha, float beta,
+                                           float C, int blackwhite, float* v_out, float* dir_out,
+                                           float* lambda_out, int device)
+{
+    if (!Dxx || !Dxy || !Dxz || !Dyy || !Dyz || !Dzz || !v_out || n < 1) return fail(FRANGI_GPU_EINVAL, "bad argument");
+    RC(check_device(device));
+    CK(cudaSetDevice(device));
+    const float* host[6] = { Dxx, Dxy, Dxz, Dyy, Dyz, Dzz };
+    float* d[6] = { nullptr };
+    float *dv = nullptr, *ddir = nullptr, *dlam = nullptr;
+    int rc = 0;
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 6 && e == cudaSuccess; ++k) {
+        e = cudaMalloc(&d[k], (size_t)n * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(d[k], host[k], (size_t)n * 4, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&dv, (size_t)n * 4);
+    if (e == cudaSuccess && dir_out) e = cudaMalloc(&ddir, (size_t)n * 12);
+    if (e == cudaSuccess && lambda_out) e = cudaMalloc(&dlam, (size_t)n * 12);
+    if (e == cudaSuccess) {
+        frangi_gpu tmp;
+        tmp.alpha = alpha; tmp.beta = beta; tmp.C = C; tmp.blackwhite = blackwhite;
+        FrangiConsts k = make_consts(&tmp, 1.0f);
+        vesselness_stage_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d[0], d[1], d[2], d[3], d[4], d[5], n, k, dv,
+                                                                      ddir, dlam);
+        g_launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(v_out, dv, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && dir_out) e = cudaMemcpy(dir_out, ddir, (size_t)n * 12, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && lambda_out) e = cudaMemcpy(lambda_out, dlam, (size_t)n * 12, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(FRANGI_GPU_ECUDA, "vesselness stage: %s", cudaGetErrorString(e));
+    for (int k = 0; k < 6; ++k) cudaFree(d[k]);
+    cudaFree(dv); cudaFree(ddir); cudaFree(dlam);
+    return rc;
+}
