@@ -146,6 +146,14 @@ uint64_t frangi_gpu_launch_count(void);
 /* per-kernel-class device time of the last run on slab 0, milliseconds:
  * [0]=gauss_xy [1]=gauss_z [2]=hessian_eigen [3]=minmax/j8 [4]=halo wait; n<=8 */
 int frangi_gpu_last_timings(frangi_gpu_t* h, float* ms, int n);
+/* Keep the per-kernel event sets of the last `depth` runs (default 1) so that a
+ * benchmark can launch K runs back to back without a host sync and still read
+ * every launch's device time; frangi_gpu_last_timings then reports the MEAN over
+ * the runs recorded since this call (at most `depth`). */
+int frangi_gpu_timing_depth(frangi_gpu_t* h, int depth);
+/* The cudaStream_t (as void*) on which slab `slab` of the handle launches its
+ * kernels, so that a caller can bracket runs with its own CUDA events. */
+void* frangi_gpu_stream(frangi_gpu_t* h, int slab);
 const char* frangi_gpu_last_error(void);
 const char* frangi_gpu_version(void);
 

@@ -180,7 +180,8 @@ struct Slab {
     int* hMinMax = nullptr;   // pinned
     cudaStream_t s_main = nullptr, s_comm = nullptr;
     cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
-    std::vector<cudaEvent_t> ev_time;   // 4 per scale + 2
+    std::vector<cudaEvent_t> ev_all;    // timing_depth sets of (4 per scale + 2) events
+    cudaEvent_t* ev_time = nullptr;     // the set of the run being recorded
     ncclx::ncclComm_t comm = nullptr;
 };
 
@@ -198,6 +199,8 @@ struct frangi_gpu {
     std::vector<ScalePlan> scales;
     std::vector<Slab> slabs;     // slabs driven by this process
     bool ran = false;
+    int timing_depth = 1;        // event sets kept per slab
+    long long runs_recorded = 0; // runs since the last frangi_gpu_timing_depth call
     float last_ms[8] = { 0 };
 };
 
@@ -211,7 +214,7 @@ void free_slab(Slab& s)
     cudaFree(s.dVx); cudaFree(s.dVy); cudaFree(s.dVz); cudaFree(s.dScale); cudaFree(s.dJ8);
     cudaFree(s.dDir); cudaFree(s.dMinMax);
     if (s.hMinMax) cudaFreeHost(s.hMinMax);
-    for (auto e : s.ev_time) cudaEventDestroy(e);
+    for (auto e : s.ev_all) cudaEventDestroy(e);
     if (s.ev_boundary) cudaEventDestroy(s.ev_boundary);
     if (s.ev_halo) cudaEventDestroy(s.ev_halo);
     if (s.s_main) cudaStreamDestroy(s.s_main);
@@ -276,8 +279,9 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     CK(cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&s.ev_boundary, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_halo, cudaEventDisableTiming));
-    s.ev_time.resize(4 * H->scales.size() + 2);
-    for (auto& e : s.ev_time) CK(cudaEventCreate(&e));
+    s.ev_all.resize(4 * H->scales.size() + 2);
+    for (auto& e : s.ev_all) CK(cudaEventCreate(&e));
+    s.ev_time = s.ev_all.data();
     CK(cudaMalloc(&s.dI, (size_t)s.voxels));
     CK(cudaMalloc(&s.dFxy, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
     CK(cudaMalloc(&s.dF, sizeof(float) * (size_t)H->fplane * (s.fe - s.fb)));
@@ -406,9 +410,12 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
 {
     const int S = (int)H->scales.size();
     const bool multi = H->nslabs_total > 1;
+    const int ev_set = (int)(H->runs_recorded % H->timing_depth);
+    H->runs_recorded++;
     for (size_t k = 0; k < H->slabs.size(); ++k) {
         Slab& s = H->slabs[k];
         CK(cudaSetDevice(s.dev));
+        s.ev_time = s.ev_all.data() + (size_t)ev_set * (4 * S + 2);
         s.hMinMax[0] = 0x7f7fffff;            // FLT_MAX  (frangi.cpp:176)
         s.hMinMax[1] = (int)0xff7fffffu;      // -FLT_MAX (frangi.cpp:177)
         CK(cudaMemcpyAsync(s.dMinMax, s.hMinMax, 2 * sizeof(int), cudaMemcpyHostToDevice, s.s_main));
@@ -501,21 +508,26 @@ int collect(frangi_gpu* H, float* Jmin, float* Jmax)
     std::memcpy(&hi, &s0.hMinMax[1], 4);
     if (Jmin) *Jmin = lo;
     if (Jmax) *Jmax = hi;
-    // per-class device times of slab 0
+    // per-class device times of slab 0: mean over the recorded runs (at most timing_depth)
     const int S = (int)H->scales.size();
     std::memset(H->last_ms, 0, sizeof H->last_ms);
     CK(cudaSetDevice(s0.dev));
-    for (int si = 0; si < S; ++si) {
+    const int nsets = (int)std::min<long long>(H->runs_recorded, H->timing_depth);
+    for (int r = 0; r < nsets; ++r) {
+        const cudaEvent_t* ev = s0.ev_all.data() + (size_t)r * (4 * S + 2);
         float t;
-        cudaEvent_t prev = si == 0 ? s0.ev_time[0] : s0.ev_time[4 * si];
-        CK(cudaEventElapsedTime(&t, prev, s0.ev_time[1 + 4 * si])); H->last_ms[0] += t;
-        CK(cudaEventElapsedTime(&t, s0.ev_time[1 + 4 * si], s0.ev_time[2 + 4 * si])); H->last_ms[4] += t;
-        CK(cudaEventElapsedTime(&t, s0.ev_time[2 + 4 * si], s0.ev_time[3 + 4 * si])); H->last_ms[1] += t;
-        CK(cudaEventElapsedTime(&t, s0.ev_time[3 + 4 * si], s0.ev_time[4 + 4 * si])); H->last_ms[2] += t;
+        for (int si = 0; si < S; ++si) {
+            cudaEvent_t prev = si == 0 ? ev[0] : ev[4 * si];
+            CK(cudaEventElapsedTime(&t, prev, ev[1 + 4 * si])); H->last_ms[0] += t;
+            CK(cudaEventElapsedTime(&t, ev[1 + 4 * si], ev[2 + 4 * si])); H->last_ms[4] += t;
+            CK(cudaEventElapsedTime(&t, ev[2 + 4 * si], ev[3 + 4 * si])); H->last_ms[1] += t;
+            CK(cudaEventElapsedTime(&t, ev[3 + 4 * si], ev[4 + 4 * si])); H->last_ms[2] += t;
+        }
+        CK(cudaEventElapsedTime(&t, ev[4 * S], ev[4 * S + 1])); H->last_ms[3] += t;
+        CK(cudaEventElapsedTime(&t, ev[0], ev[4 * S + 1])); H->last_ms[5] += t;
     }
-    float t;
-    CK(cudaEventElapsedTime(&t, s0.ev_time[4 * S], s0.ev_time[4 * S + 1])); H->last_ms[3] = t;
-    CK(cudaEventElapsedTime(&t, s0.ev_time[0], s0.ev_time[4 * S + 1])); H->last_ms[5] = t;
+    if (nsets > 0)
+        for (int i = 0; i < 6; ++i) H->last_ms[i] /= (float)nsets;
     return 0;
 }
 
@@ -757,6 +769,31 @@ FRANGI_API int frangi_gpu_last_timings(frangi_gpu_t* H, float* ms, int n)
     if (!H || !ms) return fail(FRANGI_GPU_EINVAL, "NULL argument");
     for (int i = 0; i < n && i < 8; ++i) ms[i] = H->last_ms[i];
     return 0;
+}
+
+FRANGI_API int frangi_gpu_timing_depth(frangi_gpu_t* H, int depth)
+{
+    if (!H || depth < 1 || depth > 4096) return fail(FRANGI_GPU_EINVAL, "timing depth must be 1..4096");
+    RC(sync_all(H));
+    const size_t per = 4 * H->scales.size() + 2;
+    for (auto& s : H->slabs) {
+        CK(cudaSetDevice(s.dev));
+        while (s.ev_all.size() < per * (size_t)depth) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            s.ev_all.push_back(e);
+        }
+        s.ev_time = s.ev_all.data();
+    }
+    H->timing_depth = depth;
+    H->runs_recorded = 0;
+    return 0;
+}
+
+FRANGI_API void* frangi_gpu_stream(frangi_gpu_t* H, int slab)
+{
+    if (!H || slab < 0 || slab >= (int)H->slabs.size()) return nullptr;
+    return (void*)H->slabs[slab].s_main;
 }
 
 // ---- stage entry points --------------------------------------------------------

@@ -69,6 +69,8 @@ SYMBOLS = {
     "frangi_gpu_device_count": (C.c_int, []),
     "frangi_gpu_launch_count": (C.c_uint64, []),
     "frangi_gpu_last_timings": (C.c_int, [_VP, _f32p, C.c_int]),
+    "frangi_gpu_timing_depth": (C.c_int, [_VP, C.c_int]),
+    "frangi_gpu_stream": (_VP, [_VP, C.c_int]),
     "frangi_gpu_last_error": (C.c_char_p, []),
     "frangi_gpu_version": (C.c_char_p, []),
 }
@@ -243,6 +245,14 @@ class FrangiPlan:
         ms = (C.c_float * 8)()
         _check(self.lib.frangi_gpu_last_timings(self.handle, ms, 8))
         return dict(gauss_xy=ms[0], gauss_z=ms[1], hessian_eigen=ms[2], j8=ms[3], halo_wait=ms[4], total=ms[5])
+
+    def timing_depth(self, depth: int):
+        """Keep the event sets of the last `depth` runs; timings() then returns their mean."""
+        _check(self.lib.frangi_gpu_timing_depth(self.handle, depth))
+
+    def stream(self, slab=0) -> int:
+        """cudaStream_t of the slab's kernels as an integer (for torch.cuda.ExternalStream)."""
+        return int(self.lib.frangi_gpu_stream(self.handle, slab) or 0)
 
     def device_outputs(self, slab=0):
         o = _Outputs()
