@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libpnr_ref.so,
+compiled in place from /root/reference by `make -C oracle ref`).
+
+The reference repository ships no tests or golden vectors, so the
+fixtures that pin oracle/frangi_oracle.c are outputs of the reference itself on
+seeded inputs.  They travel with the repository; the reference does not.
+
+    python tools/make_golden.py        # needs oracle/_ref (only buildable where /root/reference exists)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import Oracle, Reference  # noqa: E402
+from pnr_b200.synth import make_volume, straight_tube, volume_hash  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+PARAMS = dict(zdist=2.0, alpha=0.5, beta=0.5, Cc=500.0)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = Reference()
+    port = Oracle()   # only for the J -> J8 rule (Advantra_plugin.cpp:2499-2512 cannot be compiled without Qt)
+
+    # ---- case A: small ragged volume, every stage stored in full ---------------------
+    I = make_volume(37, 29, 13, seed=101, n_neurites=3)
+    sig = [1.0, 2.0, 3.0]
+    F = ref.imgaussian(I, 2.0, 2.0)
+    D = ref.hessian3d(I, 2.0, 2.0)
+    R = ref.frangi3d(I, sig, **PARAMS)
+    singles = [ref.frangi3d(I, [s], **PARAMS)["J"] for s in sig]
+    np.savez_compressed(os.path.join(OUT, "case_a_stages.npz"), I=I, sigmas=np.float32(sig),
+                        F_sigma2=F, **{"H_" + k: v for k, v in D.items()},
+                        J=R["J"], Jmin=np.float32(R["Jmin"]), Jmax=np.float32(R["Jmax"]),
+                        Vx=R["Vx"], Vy=R["Vy"], Vz=R["Vz"], J_single=np.stack(singles))
+
+    # ---- case B: config-1-like volume with seeds (outputs stored in full, compressed) ---
+    I = make_volume(96, 80, 24, seed=1, n_neurites=4)
+    sig = [2.0, 4.0, 6.0]
+    R = ref.frangi3d(I, sig, **PARAMS)
+    J8 = port.j_to_j8(R["J"], R["Jmin"], R["Jmax"])
+    seeds = ref.extract_seeds(5.0, J8, R["Vx"], R["Vy"], R["Vz"])
+    Rb = ref.frangi3d(255 - I, sig, blackwhite=True, **PARAMS)
+    np.savez_compressed(os.path.join(OUT, "case_b_seeds.npz"), I=I, sigmas=np.float32(sig),
+                        J=R["J"], Jmin=np.float32(R["Jmin"]), Jmax=np.float32(R["Jmax"]),
+                        Vx=R["Vx"], Vy=R["Vy"], Vz=R["Vz"], J8=J8, seeds=seeds,
+                        J_blackwhite=Rb["J"])
+
+    # ---- case C: eigen conventions (eigen_decomposition_static) --------------------------
+    rng = np.random.default_rng(5)
+    mats = [np.zeros((3, 3)), np.diag([-1e-3, -5, -5]), np.diag([-5, -1e-3, -5]), np.diag([-5, -5, -1e-3]),
+            np.diag([3.0, -2, 1]), np.diag([2.0, -2, 1]),
+            np.array([[-2, .5, .25], [.5, -3, .75], [.25, .75, -.1]]),
+            np.array([[-2, -.5, -.25], [-.5, -3, -.75], [-.25, -.75, -.1]])]
+    for _ in range(56):
+        M = rng.normal(size=(3, 3)) * rng.choice([1e-3, 1.0, 40.0])
+        mats.append((M + M.T) / 2)
+    A = np.stack(mats)
+    V = np.empty_like(A)
+    d = np.empty((len(A), 3))
+    for i, M in enumerate(A):
+        V[i], d[i] = ref.eigen3(M)
+    np.savez_compressed(os.path.join(OUT, "case_c_eigen.npz"), A=A, V=V, d=d)
+
+    # ---- case D: SURVEY.md 8c known-answer tube, summary numbers only ---------------------
+    T = straight_tube()
+    R = ref.frangi3d(T, [2.0, 4.0, 6.0], **PARAMS)
+    singles = [ref.frangi3d(T, [s], **PARAMS) for s in (2.0, 4.0, 6.0)]
+    S = np.stack([s["J"] for s in singles])
+    J8 = port.j_to_j8(R["J"], R["Jmin"], R["Jmax"])
+    pos = R["J"] > 0
+    summary = dict(
+        input_hash=volume_hash(T), input_sum=int(T.sum()),
+        single_jmax=[float(s["Jmax"]) for s in singles],
+        jmin=float(R["Jmin"]), jmax=float(R["Jmax"]), j_sum=float(R["J"].astype(np.float64).sum()),
+        n_positive=int(pos.sum()),
+        j_32_34_16=float(R["J"][16, 34, 32]), j_32_32_17=float(R["J"][17, 32, 32]), j_centre=float(R["J"][16, 32, 32]),
+        v_centre=[int(R["Vx"][16, 32, 32]), int(R["Vy"][16, 32, 32]), int(R["Vz"][16, 32, 32])],
+        v_voxel0=[int(R["Vx"][0, 0, 0]), int(R["Vy"][0, 0, 0]), int(R["Vz"][0, 0, 0])],
+        scale_hist=[int(x) for x in np.bincount(S.argmax(0)[pos], minlength=3)],
+        j8_sum=int(J8.astype(np.int64).sum()),
+        n_seeds=int(len(ref.extract_seeds(5.0, J8, R["Vx"], R["Vy"], R["Vz"]))),
+    )
+    with open(os.path.join(OUT, "case_d_tube.json"), "w") as fh:
+        json.dump(summary, fh, indent=1)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
