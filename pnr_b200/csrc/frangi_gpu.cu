@@ -343,7 +343,7 @@ FView make_fview(frangi_gpu* H, Slab& s)
 {
     FView f;
     f.F = s.dF; f.w = H->w; f.h = H->h; f.l = H->l;
-    f.fpitch = H->fpitch; f.fplane = H->fplane; f.base = s.fb;
+    f.fpitch = H->fpitch; f.fplane = H->fplane; f.base = s.fb; f.count = s.fe - s.fb;
     return f;
 }
 
@@ -356,21 +356,48 @@ FrangiConsts make_consts(frangi_gpu* H, float sigma2)
     return k;
 }
 
-int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si)
+template <int MODE>
+int launch_voxel_t(const VoxelParams& p, int nblocks, cudaStream_t st)
+{
+    auto k = hessian_eigen_kernel<MODE>;
+    static thread_local int configured_dev[64] = { 0 };
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 64 && !configured_dev[dev]) {
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, HessTile::SMEM_BYTES));
+        configured_dev[dev] = 1;
+    }
+    k<<<nblocks, HessTile::NT, HessTile::SMEM_BYTES, st>>>(p);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// mode 0 / 1: vesselness update of scale si; mode 2: dump the six second differences into D
+int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* const* D = nullptr)
 {
     VoxelParams p;
     p.f = make_fview(H, s);
     p.J = s.dJ; p.Vx = s.dVx; p.Vy = s.dVy; p.Vz = s.dVz;
     p.scale_idx = s.dScale; p.dir = s.dDir; p.voxels = s.voxels;
+    for (int k = 0; k < 6; ++k) p.D[k] = D ? D[k] : nullptr;
     p.z_begin = s.zb; p.nz = s.ze - s.zb;
-    p.scale = si; p.first_scale = si == 0; p.last_scale = si == (int)H->scales.size() - 1;
+    p.ntx = (H->w + HessTile::TX - 1) / HessTile::TX;
+    p.nty = (H->h + HessTile::TY - 1) / HessTile::TY;
+    // enough CTAs for a few waves of 148 SMs x 2 resident CTAs; each z chunk re-stages 4 planes
+    const long long tiles = (long long)p.ntx * p.nty;
+    long long nzc = std::max<long long>(1, std::min<long long>((1184 + tiles - 1) / tiles, (p.nz + 7) / 8));
+    p.zchunk = (int)((p.nz + nzc - 1) / nzc);
+    nzc = (p.nz + p.zchunk - 1) / p.zchunk;
+    p.scale = si; p.last_scale = si == (int)H->scales.size() - 1;
+    p.vec_ok = (H->w % 4 == 0);
     p.minmax = s.dMinMax;
     p.k = make_consts(H, sp.sigma2);
-    dim3 grid((H->w + 127) / 128, H->h, s.ze - s.zb);
-    hessian_eigen_kernel<<<grid, 128, 0, s.s_main>>>(p);
-    g_launches++;
-    CK(cudaGetLastError());
-    return 0;
+    const long long nblocks = tiles * nzc;
+    if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+    if (D) return launch_voxel_t<2>(p, (int)nblocks, s.s_main);
+    if (si == 0) return launch_voxel_t<0>(p, (int)nblocks, s.s_main);
+    return launch_voxel_t<1>(p, (int)nblocks, s.s_main);
 }
 
 // Exchange the xy-smoothed boundary planes of every local slab with its z
@@ -845,19 +872,13 @@ FRANGI_API int frangi_gpu_hessian3d(const uint8_t* I_host, int w, int h, int l, 
         cudaError_t e = cudaSuccess;
         for (int k = 0; k < 6 && e == cudaSuccess; ++k) e = cudaMalloc(&dD[k], n * 4);
         if (e == cudaSuccess) {
-            HessDumpParams p;
-            p.f = make_fview(H, s);
-            for (int k = 0; k < 6; ++k) p.D[k] = dD[k];
-            p.z_begin = 0; p.sigma2 = H->scales[0].sigma2;
-            dim3 grid((w + 127) / 128, h, l);
-            hessian_dump_kernel<<<grid, 128, 0, s.s_main>>>(p);
-            g_launches++;
-            e = cudaGetLastError();
+            rc = launch_voxel(H, s, H->scales[0], 0, dD);
+            if (rc) e = cudaErrorUnknown;
         }
         for (int k = 0; k < 6 && e == cudaSuccess; ++k)
             e = cudaMemcpyAsync(host[k], dD[k], n * 4, cudaMemcpyDeviceToHost, s.s_main);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s.s_main);
-        if (e != cudaSuccess) rc = fail(FRANGI_GPU_ECUDA, "hessian3d stage: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess && !rc) rc = fail(FRANGI_GPU_ECUDA, "hessian3d stage: %s", cudaGetErrorString(e));
     }
     for (int k = 0; k < 6; ++k) cudaFree(dD[k]);
     frangi_gpu_destroy(H);

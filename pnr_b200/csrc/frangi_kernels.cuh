@@ -265,10 +265,20 @@ struct FrangiConsts {
     int blackwhite;
 };
 
-// 1 - exp(-x) for x >= 0 without cancellation (the reference evaluates
-// 1 - exp(-x) in double; in float32 the subtraction would lose everything for
-// the S term, where x ~ 1e-4 with C = 500).
-__device__ __forceinline__ float one_minus_exp_neg(float x) { return -expm1f(-x); }
+// 1 - exp(-x) for x >= 0 without cancellation (the reference evaluates it in
+// double; in float32 the subtraction would lose everything for the S term,
+// where x ~ 1e-4 with C = 500): alternating series below 1/4 (truncation
+// < 2e-6 relative), 1 - ex2 above (ex2.approx is good to 2 ulp).
+__device__ __forceinline__ float one_minus_exp_neg(float x)
+{
+    const float big = 1.0f - exp2f(-1.4426950408889634f * x);
+    float s = fmaf(x, -1.0f / 720.0f, 1.0f / 120.0f);
+    s = fmaf(x, s, -1.0f / 24.0f);
+    s = fmaf(x, s, 1.0f / 6.0f);
+    s = fmaf(x, s, -0.5f);
+    s = fmaf(x, s, 1.0f);
+    return x < 0.25f ? x * s : big;
+}
 
 struct Eig3 {
     float l1, l2, l3;   // |l1| <= |l2| <= |l3| with the reference's tie rules
@@ -277,140 +287,131 @@ struct Eig3 {
 
 __device__ __forceinline__ void swapf(float& a, float& b) { float t = a; a = b; b = t; }
 
-// Symmetric 3x3 eigen-decomposition, float32, non-iterative.
-//  1. the eigenvalue at the isolated end of the spectrum from the
-//     trigonometric (Cardano) formula, where it is well conditioned;
-//  2. its eigenvector from the best-conditioned cross product of two rows of
-//     (A - lambda I);
-//  3. the other two eigenvalues (and, when needed, eigenvector) from the 2x2
-//     projection of A on the orthogonal complement: their split is then a sum
-//     of squares, not a cancelling difference.
-// Replaces eigen_decomposition (frangi.cpp:1269-1306) semantically: returns
-// the |lambda|-sorted eigenvalues and column 0 of V.
+// Symmetric 3x3 eigen-decomposition, float32, non-iterative, ~200 instructions.
+//  1. the eigenvalue at the isolated end of the spectrum, lam = q + sgn*p*g(|r|)
+//     with g(r) = 2 cos(acos(r)/3) from a degree-5 polynomial (|err| < 3e-6:
+//     lam only has to be good enough to pick out its eigenvector, see 3);
+//  2. its eigenvector i = the largest column of adj(A - lam I) (all columns are
+//     multiples of it; the largest diagonal entry of the adjugate picks the
+//     best conditioned one);
+//  3. the other two eigenvalues from the 2x2 projection M of A on the orthogonal
+//     complement of i -- their split is sqrt(hdiff^2 + m01^2), a sum of squares,
+//     so a close pair (the tube case l2 ~ l3) is resolved to float accuracy --
+//     and the isolated eigenvalue as trace(A) - trace(M), which is second-order
+//     accurate in the error of i;
+//  4. |lambda| ordering with the reference's tie rules (frangi.cpp:1284-1304),
+//     tracking only WHICH eigenvector ends up in column 0; it is then built once.
+// Replaces eigen_decomposition (frangi.cpp:1269-1306) semantically.
 __device__ __forceinline__ void eig_sym3(float a00, float a01, float a02, float a11, float a12,
                                          float a22, Eig3& out)
 {
-    float e0, e1, e2;                    // ascending eigenvalues
-    float v0x, v0y, v0z;                 // eigenvectors of e0 / e1 / e2 (built lazily below)
-    float v1x, v1y, v1z, v2x, v2y, v2z;
     const float off = a01 * a01 + a02 * a02 + a12 * a12;
     if (off == 0.0f) {
         // Diagonal input: the reference's QL leaves the values and the identity
         // untouched, then selection-sorts ascending (first minimum wins ties).
-        e0 = a00; e1 = a11; e2 = a22;
-        v0x = 1.f; v0y = 0.f; v0z = 0.f;
-        v1x = 0.f; v1y = 1.f; v1z = 0.f;
-        v2x = 0.f; v2y = 0.f; v2z = 1.f;
-        // i = 0: pick the first strict minimum of (e0,e1,e2)
+        float e0 = a00, e1 = a11, e2 = a22;
+        int i0 = 0, i1 = 1, i2 = 2;
         int k = 0; float pv = e0;
         if (e1 < pv) { k = 1; pv = e1; }
         if (e2 < pv) { k = 2; pv = e2; }
-        if (k == 1) { swapf(e0, e1); swapf(v0x, v1x); swapf(v0y, v1y); swapf(v0z, v1z); }
-        else if (k == 2) { swapf(e0, e2); swapf(v0x, v2x); swapf(v0y, v2y); swapf(v0z, v2z); }
-        if (e2 < e1) { swapf(e1, e2); swapf(v1x, v2x); swapf(v1y, v2y); swapf(v1z, v2z); }
-    } else {
-        const float tr = a00 + a11 + a22;
-        const float q = tr * (1.0f / 3.0f);
-        const float b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
-        const float p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0f * off;
-        const float p = sqrtf(p2 * (1.0f / 6.0f));
-        const float ip = 1.0f / p;
-        const float c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip;
-        const float c01 = a01 * ip, c02 = a02 * ip, c12 = a12 * ip;
-        float hd = 0.5f * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) +
-                           c02 * (c01 * c12 - c11 * c02));
-        hd = fminf(fmaxf(hd, -1.0f), 1.0f);
-        const float phi = acosf(hd) * (1.0f / 3.0f);
-        const bool top = hd >= 0.0f;   // the largest eigenvalue is the isolated one
-        const float beta = top ? 2.0f * cosf(phi) : 2.0f * cosf(phi + 2.0943951023931953f);
-        const float lam = q + p * beta;
-        // eigenvector of the isolated eigenvalue
-        const float r00 = a00 - lam, r11 = a11 - lam, r22 = a22 - lam;
-        float cx0 = a01 * a12 - a02 * r11, cy0 = a02 * a01 - r00 * a12, cz0 = r00 * r11 - a01 * a01;  // r0 x r1
-        float cx1 = a01 * r22 - a02 * a12, cy1 = a02 * a02 - r00 * r22, cz1 = r00 * a12 - a01 * a02;  // r0 x r2
-        float cx2 = r11 * r22 - a12 * a12, cy2 = a12 * a02 - a01 * r22, cz2 = a01 * a12 - r11 * a02;  // r1 x r2
-        const float n0 = cx0 * cx0 + cy0 * cy0 + cz0 * cz0;
-        const float n1 = cx1 * cx1 + cy1 * cy1 + cz1 * cz1;
-        const float n2 = cx2 * cx2 + cy2 * cy2 + cz2 * cz2;
-        float nx = cx0, ny = cy0, nz = cz0, nn = n0;
-        if (n1 > nn) { nx = cx1; ny = cy1; nz = cz1; nn = n1; }
-        if (n2 > nn) { nx = cx2; ny = cy2; nz = cz2; nn = n2; }
-        const float inn = rsqrtf(nn);
-        const float ix = nx * inn, iy = ny * inn, iz = nz * inn;
-        // orthonormal complement (u, w) of i
-        float ux, uy, uz;
-        if (fabsf(ix) > fabsf(iy)) {
-            const float s = rsqrtf(ix * ix + iz * iz);
-            ux = -iz * s; uy = 0.0f; uz = ix * s;
-        } else {
-            const float s = rsqrtf(iy * iy + iz * iz);
-            ux = 0.0f; uy = iz * s; uz = -iy * s;
-        }
-        const float wx = iy * uz - iz * uy, wy = iz * ux - ix * uz, wz = ix * uy - iy * ux;
-        // 2x2 projection
-        const float aux = a00 * ux + a01 * uy + a02 * uz;
-        const float auy = a01 * ux + a11 * uy + a12 * uz;
-        const float auz = a02 * ux + a12 * uy + a22 * uz;
-        const float awx = a00 * wx + a01 * wy + a02 * wz;
-        const float awy = a01 * wx + a11 * wy + a12 * wz;
-        const float awz = a02 * wx + a12 * wy + a22 * wz;
-        const float m00 = ux * aux + uy * auy + uz * auz;
-        const float m01 = wx * aux + wy * auy + wz * auz;
-        const float m11 = wx * awx + wy * awy + wz * awz;
-        const float mean = 0.5f * (m00 + m11);
-        const float hdiff = 0.5f * (m00 - m11);
-        const float disc = sqrtf(hdiff * hdiff + m01 * m01);
-        const float la = mean - disc, lb = mean + disc;
-        const float li = tr - (m00 + m11);   // Rayleigh-consistent isolated eigenvalue
-        // eigenvectors of la / lb inside span(u, w)
-        // (M - l I) x = 0  ->  x orthogonal to the larger of the two rows
-        float xa0, xa1;
-        {
-            const float d0 = m00 - la, d1 = m11 - la;
-            if (fabsf(d0) >= fabsf(d1)) { xa0 = -m01; xa1 = d0; } else { xa0 = d1; xa1 = -m01; }
-            const float nrm = xa0 * xa0 + xa1 * xa1;
-            if (nrm > 0.0f) { const float s = rsqrtf(nrm); xa0 *= s; xa1 *= s; }
-            else { xa0 = 1.0f; xa1 = 0.0f; }
-        }
-        const float ax = xa0 * ux + xa1 * wx, ay = xa0 * uy + xa1 * wy, az = xa0 * uz + xa1 * wz;
-        // lb's eigenvector is orthogonal to la's inside the plane
-        const float bx = -xa1 * ux + xa0 * wx, by = -xa1 * uy + xa0 * wy, bz = -xa1 * uz + xa0 * wz;
-        if (top) {
-            e0 = la; e1 = lb; e2 = li;
-            v0x = ax; v0y = ay; v0z = az; v1x = bx; v1y = by; v1z = bz; v2x = ix; v2y = iy; v2z = iz;
-        } else {
-            e0 = li; e1 = la; e2 = lb;
-            v0x = ix; v0y = iy; v0z = iz; v1x = ax; v1y = ay; v1z = az; v2x = bx; v2y = by; v2z = bz;
-        }
-        // rounding can misorder a nearly triple eigenvalue; restore ascending order
-        if (e1 < e0) { swapf(e0, e1); swapf(v0x, v1x); swapf(v0y, v1y); swapf(v0z, v1z); }
-        if (e2 < e1) { swapf(e1, e2); swapf(v1x, v2x); swapf(v1y, v2y); swapf(v1z, v2z); }
-        if (e1 < e0) { swapf(e0, e1); swapf(v0x, v1x); swapf(v0y, v1y); swapf(v0z, v1z); }
+        if (k == 1) { swapf(e0, e1); i0 = 1; i1 = 0; }
+        else if (k == 2) { swapf(e0, e2); i0 = 2; i2 = 0; }
+        if (e2 < e1) { swapf(e1, e2); int t = i1; i1 = i2; i2 = t; }
+        float m0 = fabsf(e0), m1 = fabsf(e1), m2 = fabsf(e2);
+        if (m0 >= m1 && m0 > m2) { swapf(e0, e2); swapf(m0, m2); int t = i0; i0 = i2; i2 = t; }
+        else if (m1 >= m0 && m1 > m2) { swapf(e1, e2); swapf(m1, m2); int t = i1; i1 = i2; i2 = t; }
+        if (m0 > m1) { swapf(e0, e1); int t = i0; i0 = i1; i1 = t; }
+        out.l1 = e0; out.l2 = e1; out.l3 = e2;
+        out.vx = i0 == 0 ? 1.0f : 0.0f; out.vy = i0 == 1 ? 1.0f : 0.0f; out.vz = i0 == 2 ? 1.0f : 0.0f;
+        return;
     }
+    const float tr = a00 + a11 + a22;
+    const float q = tr * (1.0f / 3.0f);
+    const float b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+    const float p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0f * off;
+    const float ip = rsqrtf(p2 * (1.0f / 6.0f));
+    const float p = p2 * (1.0f / 6.0f) * ip;
+    const float det = b00 * (b11 * b22 - a12 * a12) - a01 * (a01 * b22 - a12 * a02) + a02 * (a01 * a12 - b11 * a02);
+    const float hd = 0.5f * det * ip * ip * ip;
+    const bool top = hd >= 0.0f;          // the largest eigenvalue is the isolated one
+    const float ar = fminf(fabsf(hd), 1.0f);
+    float g = fmaf(ar, 0.00392639779f, -0.0179447089f);
+    g = fmaf(ar, g, 0.0437316173f);
+    g = fmaf(ar, g, -0.0949838747f);
+    g = fmaf(ar, g, 0.333219108f);
+    g = fmaf(ar, g, 1.73205338f);
+    const float lam = top ? fmaf(p, g, q) : fmaf(-p, g, q);
+    // adj(A - lam I): every column is a multiple of the eigenvector
+    const float r00 = a00 - lam, r11 = a11 - lam, r22 = a22 - lam;
+    const float c00 = r11 * r22 - a12 * a12;
+    const float c11 = r00 * r22 - a02 * a02;
+    const float c22 = r00 * r11 - a01 * a01;
+    const float c01 = a02 * a12 - a01 * r22;
+    const float c02 = a01 * a12 - a02 * r11;
+    const float c12 = a01 * a02 - a12 * r00;
+    const float d0 = fabsf(c00), d1 = fabsf(c11), d2 = fabsf(c22);
+    float nx = c00, ny = c01, nz = c02;
+    if (d1 > d0 && d1 >= d2) { nx = c01; ny = c11; nz = c12; }
+    if (d2 > d0 && d2 > d1) { nx = c02; ny = c12; nz = c22; }
+    const float inn = rsqrtf(nx * nx + ny * ny + nz * nz);
+    const float ix = nx * inn, iy = ny * inn, iz = nz * inn;
+    // orthonormal complement (u, w) of i
+    const bool xbig = fabsf(ix) > fabsf(iy);
+    const float ha = xbig ? ix : iy;
+    const float su = rsqrtf(ha * ha + iz * iz);
+    const float ux = xbig ? -iz * su : 0.0f;
+    const float uy = xbig ? 0.0f : iz * su;
+    const float uz = xbig ? ix * su : -iy * su;
+    const float wx = iy * uz - iz * uy, wy = iz * ux - ix * uz, wz = ix * uy - iy * ux;
+    // 2x2 projection
+    const float aux = a00 * ux + a01 * uy + a02 * uz;
+    const float auy = a01 * ux + a11 * uy + a12 * uz;
+    const float auz = a02 * ux + a12 * uy + a22 * uz;
+    const float awx = a00 * wx + a01 * wy + a02 * wz;
+    const float awy = a01 * wx + a11 * wy + a12 * wz;
+    const float awz = a02 * wx + a12 * wy + a22 * wz;
+    const float m00 = ux * aux + uy * auy + uz * auz;
+    const float m01 = wx * aux + wy * auy + wz * auz;
+    const float m11 = wx * awx + wy * awy + wz * awz;
+    const float mean = 0.5f * (m00 + m11);
+    const float hdiff = 0.5f * (m00 - m11);
+    const float disc = sqrtf(hdiff * hdiff + m01 * m01);
+    const float la = mean - disc, lb = mean + disc;
+    const float li = tr - (m00 + m11);   // Rayleigh-consistent isolated eigenvalue
+    // ascending triple and which vector belongs to each: 0 = i, 1 = in-plane of la, 2 = in-plane of lb
+    float e0 = top ? la : li, e1 = top ? lb : la, e2 = top ? li : lb;
+    int w0 = top ? 1 : 0, w1 = top ? 2 : 1, w2 = top ? 0 : 2;
     // re-order by absolute value with the reference's rules (frangi.cpp:1284-1304)
-    float d0 = e0, d1 = e1, d2 = e2;
-    float m0 = fabsf(d0), m1 = fabsf(d1), m2 = fabsf(d2);
-    if (m0 >= m1 && m0 > m2) {
-        swapf(d0, d2); swapf(m0, m2); swapf(v0x, v2x); swapf(v0y, v2y); swapf(v0z, v2z);
-    } else if (m1 >= m0 && m1 > m2) {
-        swapf(d1, d2); swapf(m1, m2); swapf(v1x, v2x); swapf(v1y, v2y); swapf(v1z, v2z);
-    }
-    if (m0 > m1) {
-        swapf(d0, d1); swapf(m0, m1); swapf(v0x, v1x); swapf(v0y, v1y); swapf(v0z, v1z);
-    }
-    out.l1 = d0; out.l2 = d1; out.l3 = d2;
-    out.vx = v0x; out.vy = v0y; out.vz = v0z;
+    float m0 = fabsf(e0), m1 = fabsf(e1), m2 = fabsf(e2);
+    if (m0 >= m1 && m0 > m2) { swapf(e0, e2); swapf(m0, m2); const int t = w0; w0 = w2; w2 = t; }
+    else if (m1 >= m0 && m1 > m2) { swapf(e1, e2); swapf(m1, m2); const int t = w1; w1 = w2; w2 = t; }
+    if (m0 > m1) { swapf(e0, e1); const int t = w0; w0 = w1; w1 = t; }
+    out.l1 = e0; out.l2 = e1; out.l3 = e2;
+    // eigenvector of e0: i itself, or the null vector of (M - e0 I) inside span(u, w)
+    const float f0 = m00 - e0, f1 = m11 - e0;
+    const bool r0 = fabsf(f0) >= fabsf(f1);
+    float xa0 = r0 ? -m01 : f1;
+    float xa1 = r0 ? f0 : -m01;
+    const float nrm = xa0 * xa0 + xa1 * xa1;
+    const float sn = rsqrtf(nrm);
+    xa0 = nrm > 0.0f ? xa0 * sn : 1.0f;
+    xa1 = nrm > 0.0f ? xa1 * sn : 0.0f;
+    const float px = xa0 * ux + xa1 * wx, py = xa0 * uy + xa1 * wy, pz = xa0 * uz + xa1 * wz;
+    out.vx = w0 == 0 ? ix : px;
+    out.vy = w0 == 0 ? iy : py;
+    out.vz = w0 == 0 ? iz : pz;
 }
 
 // Frangi vesselness from |lambda|-sorted eigenvalues (frangi.cpp:206-231).
 __device__ __forceinline__ float vesselness(const Eig3& e, const FrangiConsts& k)
 {
     const float a1 = fabsf(e.l1), a2 = fabsf(e.l2), a3 = fabsf(e.l3);
-    const float Ra = a2 / a3;
-    const float Rb = a1 / sqrtf(a2 * a3);
+    const float i3 = __fdividef(1.0f, a3);
+    const float Ra = a2 * i3;
+    const float Rb2 = a1 * a1 * i3 * __fdividef(1.0f, a2);    // (|l1| / sqrt(|l2 l3|))^2
     const float S2 = a1 * a1 + a2 * a2 + a3 * a3;
     const float tRa = one_minus_exp_neg(Ra * Ra * k.inv_2a2);
-    const float tRb = expf(-(Rb * Rb) * k.inv_2b2);
+    const float tRb = exp2f(-1.4426950408889634f * Rb2 * k.inv_2b2);
     const float tS = one_minus_exp_neg(S2 * k.inv_2c2);
     float v = tRa * tRb * tS;
     if (k.blackwhite) {
@@ -440,36 +441,30 @@ __device__ __forceinline__ uint8_t dir_code(float c)
 // applies the same rule to the first-difference field; then * sigma^2.
 // Coordinates are GLOBAL (slab faces are not volume faces).
 // ---------------------------------------------------------------------------
-struct FView {
-    const float* F;     // plane 0 = global plane base
-    int w, h, l;
-    int fpitch;
-    long long fplane;
-    int base;
-    __device__ __forceinline__ float at(int x, int y, int z) const
-    {
-        return __ldg(F + (long long)(z - base) * fplane + (long long)y * fpitch + x);
-    }
-};
-
 __device__ __forceinline__ float face_scale(int c, int n) { return (c == 0 || c == n - 1) ? 1.0f : 0.5f; }
 
-__device__ __forceinline__ float d_dx(const FView& f, int x, int y, int z)
+struct Hess { float xx, xy, xz, yy, yz, zz; };
+
+// Generic form for voxels within two steps of a volume face.  `Field` provides
+// at(x, y, z) for any coordinate inside the volume and within +-2 of the voxel.
+template <class Field>
+__device__ __forceinline__ float d_dx(const Field& f, int x, int y, int z)
 {
     return __fmul_rn(face_scale(x, f.w), __fsub_rn(f.at(min(x + 1, f.w - 1), y, z), f.at(max(x - 1, 0), y, z)));
 }
-__device__ __forceinline__ float d_dy(const FView& f, int x, int y, int z)
+template <class Field>
+__device__ __forceinline__ float d_dy(const Field& f, int x, int y, int z)
 {
     return __fmul_rn(face_scale(y, f.h), __fsub_rn(f.at(x, min(y + 1, f.h - 1), z), f.at(x, max(y - 1, 0), z)));
 }
-__device__ __forceinline__ float d_dz(const FView& f, int x, int y, int z)
+template <class Field>
+__device__ __forceinline__ float d_dz(const Field& f, int x, int y, int z)
 {
     return __fmul_rn(face_scale(z, f.l), __fsub_rn(f.at(x, y, min(z + 1, f.l - 1)), f.at(x, y, max(z - 1, 0))));
 }
 
-struct Hess { float xx, xy, xz, yy, yz, zz; };
-
-__device__ __forceinline__ Hess hessian_at(const FView& f, int x, int y, int z, float sigma2)
+template <class Field>
+__device__ __noinline__ Hess hessian_at_face(const Field& f, int x, int y, int z, float sigma2)
 {
     const int xl = max(x - 1, 0), xh = min(x + 1, f.w - 1);
     const int yl = max(y - 1, 0), yh = min(y + 1, f.h - 1);
@@ -486,14 +481,53 @@ __device__ __forceinline__ Hess hessian_at(const FView& f, int x, int y, int z, 
 }
 
 // ---------------------------------------------------------------------------
-// K3: Hessian -> eigen -> vesselness -> running max over scales.
+// K3: Hessian -> eigen -> vesselness -> running max over scales, z-marching.
+//
+// A CTA owns a 128 x 16 column of voxels and marches along z through its chunk.
+// The five planes z-2 .. z+2 of the smoothed volume F that the twice-applied
+// central difference touches live in a six-slot shared-memory ring of
+// (16+4) x (128+4) tiles (slot = plane mod 6, so the plane being staged never
+// aliases one being read and one __syncthreads per plane suffices); tile
+// entries are F at CLAMPED coordinates, which is exactly what the face rules
+// read.  The next plane's tile is fetched from global memory into registers
+// before the current plane is processed and parked in the ring afterwards, so
+// the loads are in flight during the ~300-instruction per-voxel stage.
+// A thread produces 4 consecutive x voxels of 2 rows per plane: window rows are
+// read with 128-bit / 64-bit shared loads (6.5 loads per voxel) and results
+// leave as float4 / uchar4 stores.  Voxels at least two steps from every face
+// take the closed interior form, bit-identical to the generic one:
+//   Dxx = ((F[x+2]-F[x]) - (F[x]-F[x-2])) * (sigma^2/4), Dxy = ((F[+1,+1]-F[-1,+1])
+//   - (F[+1,-1]-F[-1,-1])) * (sigma^2/4)   (halving is exact, so the 0.5 factors
+//   commute with the roundings of frangi.cpp:308-381);
+// the rest go through hessian_at_face on the same ring.
+//
 // Outputs are dense over the slab's own planes [z_begin, z_begin + nz).
-// first_scale: store unconditionally (frangi.cpp:234-252); otherwise overwrite
-// only on a strictly greater response (frangi.cpp:254-271).
+// MODE 0: first scale, store unconditionally (frangi.cpp:234-252);
+// MODE 1: later scale, overwrite only on a strictly greater response (:254-271);
+// MODE 2: stage dump of the six second differences (hessian3d parity).
 // minmax[0] = bits of min J (taken on the first scale),
 // minmax[1] = bits of max J (taken on the last scale).  J >= 0, so the int
 // order of the bit patterns is the float order.
 // ---------------------------------------------------------------------------
+struct FView {
+    const float* F;     // plane 0 = global plane base
+    int w, h, l;
+    int fpitch;
+    long long fplane;
+    int base;           // first resident plane
+    int count;          // resident planes
+};
+
+struct HessTile {
+    static constexpr int TX = 128, TY = 16, NT = 256;
+    static constexpr int PW = TX + 4;            // 132 floats per tile row (16-byte multiple)
+    static constexpr int PH = TY + 4;
+    static constexpr int PLANE = PW * PH;        // 2640 floats
+    static constexpr int SLOTS = 6;
+    static constexpr int LOADS = (PLANE + NT - 1) / NT;   // 11 staged values per thread
+    static constexpr int SMEM_BYTES = SLOTS * PLANE * 4;  // 63360
+};
+
 struct VoxelParams {
     FView f;
     float* J;
@@ -502,80 +536,231 @@ struct VoxelParams {
     uint8_t* Vz;
     uint8_t* scale_idx;   // nullable
     float* dir;           // nullable, 3 planar volumes of `voxels` floats
+    float* D[6];          // MODE 2 only: Dzz, Dyy, Dyz, Dxx, Dxy, Dxz (reference argument order)
     long long voxels;     // own voxels
-    int z_begin, nz;
+    int z_begin, nz;      // own planes
+    int zchunk;           // planes per CTA along z
+    int ntx, nty;         // tiles along x and y
     int scale;            // index of this scale
-    int first_scale, last_scale;
+    int last_scale;
+    int vec_ok;           // w % 4 == 0: quads are aligned for 128-bit / 32-bit vector stores
     int* minmax;
     FrangiConsts k;
 };
 
-__global__ void __launch_bounds__(128)
-hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
-{
-    const int x = blockIdx.x * 128 + threadIdx.x;
-    const int y = blockIdx.y;
-    const int zl = blockIdx.z;
-    float jval = 0.0f;
-    const bool active = x < p.f.w;
-    if (active) {
-        const int z = p.z_begin + zl;
-        const Hess H = hessian_at(p.f, x, y, z, p.k.sigma2);
-        Eig3 e;
-        eig_sym3(H.xx, H.xy, H.xz, H.yy, H.yz, H.zz, e);
-        const float v = vesselness(e, p.k);
-        const long long i = ((long long)zl * p.f.h + y) * p.f.w + x;
-        bool write = p.first_scale;
-        float jold = 0.0f;
-        if (!write) { jold = p.J[i]; write = v > jold; }
-        if (write) {
-            p.J[i] = v;
-            p.Vx[i] = dir_code(e.vx);
-            p.Vy[i] = dir_code(e.vy);
-            p.Vz[i] = dir_code(e.vz);
-            if (p.scale_idx) p.scale_idx[i] = (uint8_t)p.scale;
-            if (p.dir) {
-                p.dir[i] = e.vx;
-                p.dir[p.voxels + i] = e.vy;
-                p.dir[2 * p.voxels + i] = e.vz;
-            }
-            jval = v;
-        } else {
-            jval = jold;
-        }
+// shared-memory ring as a Field for hessian_at_face
+struct RingField {
+    const float* ring;
+    int w, h, l;
+    int x0, y0;           // global coordinates of tile entry (0, 0)
+    __device__ __forceinline__ float at(int x, int y, int z) const
+    {
+        return ring[((z + HessTile::SLOTS) % HessTile::SLOTS) * HessTile::PLANE + (y - y0) * HessTile::PW + (x - x0)];
     }
-    // warp-shuffle reductions of min (first scale) and max (last scale)
-    if (p.first_scale) {
-        float m = active ? jval : 3.4e38f;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, s));
-        if ((threadIdx.x & 31) == 0) atomicMin(p.minmax + 0, __float_as_int(m));
-    }
-    if (p.last_scale) {
-        float m = active ? jval : 0.0f;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-        if ((threadIdx.x & 31) == 0) atomicMax(p.minmax + 1, __float_as_int(m));
-    }
-}
-
-// Debug / stage kernel: dump the six second-difference volumes (hessian3d parity).
-struct HessDumpParams {
-    FView f;
-    float* D[6];   // Dzz, Dyy, Dyz, Dxx, Dxy, Dxz (reference argument order), dense
-    int z_begin;
-    float sigma2;
 };
 
-__global__ void __launch_bounds__(128) hessian_dump_kernel(const __grid_constant__ HessDumpParams p)
+template <int MODE>
+__global__ void __launch_bounds__(HessTile::NT, 2)
+hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
 {
-    const int x = blockIdx.x * 128 + threadIdx.x;
-    if (x >= p.f.w) return;
-    const int y = blockIdx.y, zl = blockIdx.z;
-    const Hess H = hessian_at(p.f, x, y, p.z_begin + zl, p.sigma2);
-    const long long i = ((long long)zl * p.f.h + y) * p.f.w + x;
-    p.D[0][i] = H.zz; p.D[1][i] = H.yy; p.D[2][i] = H.yz;
-    p.D[3][i] = H.xx; p.D[4][i] = H.xy; p.D[5][i] = H.xz;
+    using T = HessTile;
+    extern __shared__ __align__(16) float ring[];
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    int bid = blockIdx.x;
+    const int bx = bid % p.ntx; bid /= p.ntx;
+    const int by = bid % p.nty;
+    const int bz = bid / p.nty;
+    const int x0 = bx * T::TX - 2, y0 = by * T::TY - 2;       // global coordinates of tile entry (0, 0)
+    const int zs = p.z_begin + bz * p.zchunk;                  // first centre plane
+    const int ze = min(zs + p.zchunk, p.z_begin + p.nz);       // one past the last
+    const int w = p.f.w, h = p.f.h, l = p.f.l;
+
+    // staging map: this thread's k-th tile entry and its clamped global offset (plane-independent)
+    int s_off[T::LOADS];
+    long long g_off[T::LOADS];
+#pragma unroll
+    for (int k = 0; k < T::LOADS; ++k) {
+        const int e = tid + k * T::NT;
+        const int r = e / T::PW, c = e - r * T::PW;
+        s_off[k] = e < T::PLANE ? e : -1;
+        g_off[k] = (long long)clampi(y0 + r, 0, h - 1) * p.f.fpitch + clampi(x0 + c, 0, w - 1);
+    }
+    float stage[T::LOADS];
+    auto fetch = [&](int plane) {
+        const int zc = clampi(clampi(plane, 0, l - 1) - p.f.base, 0, p.f.count - 1);
+        const float* __restrict__ src = p.f.F + (long long)zc * p.f.fplane;
+#pragma unroll
+        for (int k = 0; k < T::LOADS; ++k)
+            if (s_off[k] >= 0) stage[k] = __ldg(src + g_off[k]);
+    };
+    auto park = [&](int plane) {
+        float* dst = ring + ((plane + T::SLOTS) % T::SLOTS) * T::PLANE;
+#pragma unroll
+        for (int k = 0; k < T::LOADS; ++k)
+            if (s_off[k] >= 0) dst[s_off[k]] = stage[k];
+    };
+
+    // prologue: planes zs-2 .. zs+1 into the ring, zs+2 in flight
+    for (int q = zs - 2; q <= zs + 1; ++q) { fetch(q); park(q); }
+    fetch(zs + 2);
+
+    const int xq = bx * T::TX + 4 * tx;          // first of this thread's 4 x voxels
+    float vmin = 3.4e38f, vmax = 0.0f;
+
+    for (int z = zs; z < ze; ++z) {
+        park(z + 2);
+        __syncthreads();                          // plane z+2 visible; everyone is done with plane z-3's slot
+        if (z + 1 < ze) fetch(z + 3);
+
+        const float* P0 = ring + ((z + T::SLOTS) % T::SLOTS) * T::PLANE;
+        const float* Pm1 = ring + ((z - 1 + T::SLOTS) % T::SLOTS) * T::PLANE;
+        const float* Pp1 = ring + ((z + 1 + T::SLOTS) % T::SLOTS) * T::PLANE;
+        const float* Pm2 = ring + ((z - 2 + T::SLOTS) % T::SLOTS) * T::PLANE;
+        const float* Pp2 = ring + ((z + 2 + T::SLOTS) % T::SLOTS) * T::PLANE;
+        const bool z_in = z >= 2 && z <= l - 3;
+        const float qs = 0.25f * p.k.sigma2;
+
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int yl = ty + 8 * half;         // row inside the tile
+            const int y = by * T::TY + yl;
+            if (y >= h || xq >= w) continue;
+            Hess H[4];
+            const bool interior = z_in && y >= 2 && y <= h - 3 && xq >= 2 && xq + 3 <= w - 3;
+            if (interior) {
+                const int o = (yl + 2) * T::PW + 4 * tx;      // tile entry of (x = xq - 2, y)
+                // plane z: rows y-1, y, y+1 over x-2 .. x+5; rows y-2, y+2 over x .. x+3
+                float a[8], b[8], c[8];
+                *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(P0 + o - T::PW);
+                *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(P0 + o - T::PW + 4);
+                *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(P0 + o);
+                *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(P0 + o + 4);
+                *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(P0 + o + T::PW);
+                *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(P0 + o + T::PW + 4);
+                float t2[4], u2[4];
+                *reinterpret_cast<float2*>(t2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 2);
+                *reinterpret_cast<float2*>(t2 + 2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 4);
+                *reinterpret_cast<float2*>(u2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 2);
+                *reinterpret_cast<float2*>(u2 + 2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float f0 = b[j + 2];
+                    H[j].xx = __fmul_rn(__fsub_rn(__fsub_rn(b[j + 4], f0), __fsub_rn(f0, b[j])), qs);
+                    H[j].yy = __fmul_rn(__fsub_rn(__fsub_rn(u2[j], f0), __fsub_rn(f0, t2[j])), qs);
+                    H[j].xy = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 3], c[j + 1]), __fsub_rn(a[j + 3], a[j + 1])), qs);
+                }
+                // planes z-1, z+1: row y over x-1 .. x+4 (loaded as x-2 .. x+5), rows y-1, y+1 over x .. x+3
+                float m[8], n[8], mu[4], md[4], nu[4], nd[4];
+                *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(Pm1 + o);
+                *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(Pm1 + o + 4);
+                *reinterpret_cast<float4*>(n) = *reinterpret_cast<const float4*>(Pp1 + o);
+                *reinterpret_cast<float4*>(n + 4) = *reinterpret_cast<const float4*>(Pp1 + o + 4);
+                *reinterpret_cast<float2*>(mu) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 2);
+                *reinterpret_cast<float2*>(mu + 2) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 4);
+                *reinterpret_cast<float2*>(md) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 2);
+                *reinterpret_cast<float2*>(md + 2) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 4);
+                *reinterpret_cast<float2*>(nu) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 2);
+                *reinterpret_cast<float2*>(nu + 2) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 4);
+                *reinterpret_cast<float2*>(nd) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 2);
+                *reinterpret_cast<float2*>(nd + 2) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 4);
+                float k2[4], l2[4];
+                *reinterpret_cast<float2*>(k2) = *reinterpret_cast<const float2*>(Pm2 + o + 2);
+                *reinterpret_cast<float2*>(k2 + 2) = *reinterpret_cast<const float2*>(Pm2 + o + 4);
+                *reinterpret_cast<float2*>(l2) = *reinterpret_cast<const float2*>(Pp2 + o + 2);
+                *reinterpret_cast<float2*>(l2 + 2) = *reinterpret_cast<const float2*>(Pp2 + o + 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float f0 = b[j + 2];
+                    H[j].xz = __fmul_rn(__fsub_rn(__fsub_rn(n[j + 3], n[j + 1]), __fsub_rn(m[j + 3], m[j + 1])), qs);
+                    H[j].yz = __fmul_rn(__fsub_rn(__fsub_rn(nd[j], nu[j]), __fsub_rn(md[j], mu[j])), qs);
+                    H[j].zz = __fmul_rn(__fsub_rn(__fsub_rn(l2[j], f0), __fsub_rn(f0, k2[j])), qs);
+                }
+            } else {
+                RingField rf;
+                rf.ring = ring; rf.w = w; rf.h = h; rf.l = l; rf.x0 = x0; rf.y0 = y0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (xq + j < w) H[j] = hessian_at_face(rf, xq + j, y, z, p.k.sigma2);
+                    else H[j] = Hess{ 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+            }
+
+            const long long i0 = ((long long)(z - p.z_begin) * h + y) * w + xq;
+            if (MODE == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (xq + j < w) {
+                        p.D[0][i0 + j] = H[j].zz; p.D[1][i0 + j] = H[j].yy; p.D[2][i0 + j] = H[j].yz;
+                        p.D[3][i0 + j] = H[j].xx; p.D[4][i0 + j] = H[j].xy; p.D[5][i0 + j] = H[j].xz;
+                    }
+                continue;
+            }
+            const bool full = p.vec_ok && xq + 3 < w;
+            float jold[4] = { 0.f, 0.f, 0.f, 0.f };
+            if (MODE == 1) {
+                if (full) *reinterpret_cast<float4*>(jold) = *reinterpret_cast<const float4*>(p.J + i0);
+                else
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (xq + j < w) jold[j] = p.J[i0 + j];
+            }
+            float jn[4];
+            uint8_t cx[4], cy[4], cz[4];
+            float ex[4], ey[4], ez[4];
+            bool wr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                Eig3 e;
+                eig_sym3(H[j].xx, H[j].xy, H[j].xz, H[j].yy, H[j].yz, H[j].zz, e);
+                const float v = vesselness(e, p.k);
+                wr[j] = (MODE == 0 || v > jold[j]) && (xq + j < w);
+                jn[j] = wr[j] ? v : jold[j];
+                cx[j] = dir_code(e.vx); cy[j] = dir_code(e.vy); cz[j] = dir_code(e.vz);
+                ex[j] = e.vx; ey[j] = e.vy; ez[j] = e.vz;
+                if (xq + j < w) { vmin = fminf(vmin, jn[j]); vmax = fmaxf(vmax, jn[j]); }
+            }
+            if (MODE == 0 && full) {
+                *reinterpret_cast<float4*>(p.J + i0) = make_float4(jn[0], jn[1], jn[2], jn[3]);
+                *reinterpret_cast<uchar4*>(p.Vx + i0) = make_uchar4(cx[0], cx[1], cx[2], cx[3]);
+                *reinterpret_cast<uchar4*>(p.Vy + i0) = make_uchar4(cy[0], cy[1], cy[2], cy[3]);
+                *reinterpret_cast<uchar4*>(p.Vz + i0) = make_uchar4(cz[0], cz[1], cz[2], cz[3]);
+                if (p.scale_idx) *reinterpret_cast<uchar4*>(p.scale_idx + i0) = make_uchar4(0, 0, 0, 0);
+                if (p.dir) {
+                    *reinterpret_cast<float4*>(p.dir + i0) = make_float4(ex[0], ex[1], ex[2], ex[3]);
+                    *reinterpret_cast<float4*>(p.dir + p.voxels + i0) = make_float4(ey[0], ey[1], ey[2], ey[3]);
+                    *reinterpret_cast<float4*>(p.dir + 2 * p.voxels + i0) = make_float4(ez[0], ez[1], ez[2], ez[3]);
+                }
+            } else {
+                if (MODE == 1 && full) {
+                    if (wr[0] || wr[1] || wr[2] || wr[3])
+                        *reinterpret_cast<float4*>(p.J + i0) = make_float4(jn[0], jn[1], jn[2], jn[3]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (wr[j]) {
+                        if (!(MODE == 1 && full)) p.J[i0 + j] = jn[j];
+                        p.Vx[i0 + j] = cx[j]; p.Vy[i0 + j] = cy[j]; p.Vz[i0 + j] = cz[j];
+                        if (p.scale_idx) p.scale_idx[i0 + j] = (uint8_t)p.scale;
+                        if (p.dir) {
+                            p.dir[i0 + j] = ex[j];
+                            p.dir[p.voxels + i0 + j] = ey[j];
+                            p.dir[2 * p.voxels + i0 + j] = ez[j];
+                        }
+                    }
+            }
+        }
+    }
+    if (MODE == 2) return;
+    // warp-shuffle reductions of min (first scale) and max (last scale), one atomic per warp
+    if (MODE == 0) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, s));
+        if (tx == 0 && vmin < 3.0e38f) atomicMin(p.minmax + 0, __float_as_int(vmin));
+    }
+    if (p.last_scale) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
+        if (tx == 0) atomicMax(p.minmax + 1, __float_as_int(vmax));
+    }
 }
 
 // Stage kernel: eigen + vesselness on caller-supplied Hessians.
