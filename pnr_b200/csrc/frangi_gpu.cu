@@ -244,7 +244,7 @@ int plan_common(frangi_gpu* H, const float* sigmas, int nsig, float zdist, float
     if (!sigmas || nsig < 1 || nsig > 64) return fail(FRANGI_GPU_EINVAL, "nsig must be 1..64");
     if (w < 2 || h < 2 || l < 2)
         return fail(FRANGI_GPU_EINVAL, "frangi3d needs w,h,l >= 2 (got %d,%d,%d); 2-D images are out of scope", w, h, l);
-    if (h > 65535) return fail(FRANGI_GPU_EINVAL, "h > 65535 not supported");
+    if ((long long)((w + 31) / 32 * 32) * h > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "plane of %d x %d is too large", w, h);
     if (!(zdist > 0)) return fail(FRANGI_GPU_EINVAL, "zdist must be > 0");
     H->w = w; H->h = h; H->l = l;
     H->fpitch = (w + 31) / 32 * 32;
@@ -357,20 +357,42 @@ FrangiConsts make_consts(frangi_gpu* H, float sigma2)
 }
 
 template <int MODE>
-int launch_voxel_t(const VoxelParams& p, int nblocks, cudaStream_t st)
+int launch_voxel_t(const VoxelParams& p, long long nblocks, long long nshell, cudaStream_t st)
 {
-    auto k = hessian_eigen_kernel<MODE>;
-    static thread_local int configured_dev[64] = { 0 };
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    if (dev < 64 && !configured_dev[dev]) {
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, HessTile::SMEM_BYTES));
-        configured_dev[dev] = 1;
+    if (nblocks > 0) {
+        auto k = hessian_eigen_kernel<MODE>;
+        static thread_local int configured_dev[64] = { 0 };
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        if (dev < 64 && !configured_dev[dev]) {
+            CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, HessTile::SMEM_BYTES));
+            configured_dev[dev] = 1;
+        }
+        k<<<(unsigned)nblocks, HessTile::NT, HessTile::SMEM_BYTES, st>>>(p);
+        g_launches++;
+        CK(cudaGetLastError());
     }
-    k<<<nblocks, HessTile::NT, HessTile::SMEM_BYTES, st>>>(p);
-    g_launches++;
-    CK(cudaGetLastError());
+    if (nshell > 0) {
+        hessian_eigen_shell_kernel<MODE><<<(unsigned)((nshell + 127) / 128), 128, 0, st>>>(p);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
     return 0;
+}
+
+// the coordinates 0, 1, n-2, n-1 clipped to [lo, hi) without duplicates
+int face_list(int n, int lo, int hi, int* out)
+{
+    const int cand[4] = { 0, 1, n - 2, n - 1 };
+    int k = 0;
+    for (int c : cand) {
+        if (c < lo || c >= hi) continue;
+        bool dup = false;
+        for (int q = 0; q < k; ++q) dup |= out[q] == c;
+        if (!dup) out[k++] = c;
+    }
+    for (int q = k; q < 4; ++q) out[q] = 0;
+    return k;
 }
 
 // mode 0 / 1: vesselness update of scale si; mode 2: dump the six second differences into D
@@ -393,11 +415,20 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
     p.vec_ok = (H->w % 4 == 0);
     p.minmax = s.dMinMax;
     p.k = make_consts(H, sp.sigma2);
-    const long long nblocks = tiles * nzc;
-    if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
-    if (D) return launch_voxel_t<2>(p, (int)nblocks, s.s_main);
-    if (si == 0) return launch_voxel_t<0>(p, (int)nblocks, s.s_main);
-    return launch_voxel_t<1>(p, (int)nblocks, s.s_main);
+    // the two-voxel shell next to the volume faces goes to the shell kernel
+    p.nxf = face_list(H->w, 0, H->w, p.xf);
+    p.nyf = face_list(H->h, 0, H->h, p.yf);
+    p.nzf = face_list(H->l, s.zb, s.ze, p.zf);
+    p.n_zface = (long long)H->w * H->h * p.nzf;
+    p.n_yface = (long long)H->w * p.nyf * p.nz;
+    p.n_xface = (long long)p.nxf * H->h * p.nz;
+    const long long nshell = p.n_zface + p.n_yface + p.n_xface;
+    long long nblocks = tiles * nzc;
+    if (H->w < 5 || H->h < 5 || H->l < 5) nblocks = 0;   // no voxel is two steps away from every face
+    if (nblocks > 0x7fffffffLL || (nshell + 127) / 128 > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+    if (D) return launch_voxel_t<2>(p, nblocks, nshell, s.s_main);
+    if (si == 0) return launch_voxel_t<0>(p, nblocks, nshell, s.s_main);
+    return launch_voxel_t<1>(p, nblocks, nshell, s.s_main);
 }
 
 // Exchange the xy-smoothed boundary planes of every local slab with its z

@@ -481,25 +481,32 @@ __device__ __noinline__ Hess hessian_at_face(const Field& f, int x, int y, int z
 }
 
 // ---------------------------------------------------------------------------
-// K3: Hessian -> eigen -> vesselness -> running max over scales, z-marching.
+// K3: Hessian -> eigen -> vesselness -> running max over scales.
 //
-// A CTA owns a 128 x 16 column of voxels and marches along z through its chunk.
+// Two kernels per scale share the per-voxel stage:
+//
+// K3a hessian_eigen_kernel (interior, > 98 % of the voxels of a real volume):
+// a CTA owns a 128 x 16 column of voxels and marches along z through its chunk.
 // The five planes z-2 .. z+2 of the smoothed volume F that the twice-applied
 // central difference touches live in a six-slot shared-memory ring of
 // (16+4) x (128+4) tiles (slot = plane mod 6, so the plane being staged never
-// aliases one being read and one __syncthreads per plane suffices); tile
-// entries are F at CLAMPED coordinates, which is exactly what the face rules
-// read.  The next plane's tile is fetched from global memory into registers
-// before the current plane is processed and parked in the ring afterwards, so
-// the loads are in flight during the ~300-instruction per-voxel stage.
-// A thread produces 4 consecutive x voxels of 2 rows per plane: window rows are
-// read with 128-bit / 64-bit shared loads (6.5 loads per voxel) and results
-// leave as float4 / uchar4 stores.  Voxels at least two steps from every face
-// take the closed interior form, bit-identical to the generic one:
-//   Dxx = ((F[x+2]-F[x]) - (F[x]-F[x-2])) * (sigma^2/4), Dxy = ((F[+1,+1]-F[-1,+1])
-//   - (F[+1,-1]-F[-1,-1])) * (sigma^2/4)   (halving is exact, so the 0.5 factors
-//   commute with the roundings of frangi.cpp:308-381);
-// the rest go through hessian_at_face on the same ring.
+// aliases one being read and one __syncthreads per plane suffices).  The next
+// plane's tile is fetched from global memory into registers before the current
+// plane is processed and parked in the ring afterwards, so the loads are in
+// flight during the per-voxel stage.  A thread produces 4 consecutive x voxels
+// of 2 rows per plane: window rows are read with 128-bit / 64-bit shared loads
+// (6.5 loads per voxel) and results leave as float4 / uchar4 stores.  Voxels at
+// least two steps from every volume face take the closed interior form,
+// bit-identical to the reference's two-pass form:
+//   Dxx = ((F[x+2]-F[x]) - (F[x]-F[x-2])) * (sigma^2/4),
+//   Dxy = ((F[+1,+1]-F[-1,+1]) - (F[+1,-1]-F[-1,-1])) * (sigma^2/4)
+// (halving is exact, so the 0.5 factors commute with the roundings of
+// frangi.cpp:308-381).  The kernel never touches a voxel within two steps of a
+// volume face.
+//
+// K3b hessian_eigen_shell_kernel: the two-voxel-thick shell next to the volume
+// faces (x, y < 2 or > n-3; z likewise), one thread per voxel, generic face
+// rules straight from global memory.  Runs after K3a on the same stream.
 //
 // Outputs are dense over the slab's own planes [z_begin, z_begin + nz).
 // MODE 0: first scale, store unconditionally (frangi.cpp:234-252);
@@ -516,6 +523,10 @@ struct FView {
     long long fplane;
     int base;           // first resident plane
     int count;          // resident planes
+    __device__ __forceinline__ float at(int x, int y, int z) const
+    {
+        return __ldg(F + (long long)(z - base) * fplane + (long long)y * fpitch + x);
+    }
 };
 
 struct HessTile {
@@ -539,25 +550,38 @@ struct VoxelParams {
     float* D[6];          // MODE 2 only: Dzz, Dyy, Dyz, Dxx, Dxy, Dxz (reference argument order)
     long long voxels;     // own voxels
     int z_begin, nz;      // own planes
-    int zchunk;           // planes per CTA along z
-    int ntx, nty;         // tiles along x and y
+    int zchunk;           // planes per CTA along z (K3a)
+    int ntx, nty;         // tiles along x and y (K3a)
     int scale;            // index of this scale
     int last_scale;
     int vec_ok;           // w % 4 == 0: quads are aligned for 128-bit / 32-bit vector stores
     int* minmax;
     FrangiConsts k;
+    // K3b: the face coordinates (deduplicated) and the three region sizes
+    int xf[4], yf[4], zf[4];
+    int nxf, nyf, nzf;
+    long long n_zface, n_yface, n_xface;
 };
 
-// shared-memory ring as a Field for hessian_at_face
-struct RingField {
-    const float* ring;
-    int w, h, l;
-    int x0, y0;           // global coordinates of tile entry (0, 0)
-    __device__ __forceinline__ float at(int x, int y, int z) const
-    {
-        return ring[((z + HessTile::SLOTS) % HessTile::SLOTS) * HessTile::PLANE + (y - y0) * HessTile::PW + (x - x0)];
+// one voxel's update (scalar stores); returns the value J holds afterwards
+template <int MODE>
+__device__ __forceinline__ float voxel_update(const VoxelParams& p, long long i, const Hess& H)
+{
+    Eig3 e;
+    eig_sym3(H.xx, H.xy, H.xz, H.yy, H.yz, H.zz, e);
+    const float v = vesselness(e, p.k);
+    float jold = 0.0f;
+    bool write = MODE == 0;
+    if (MODE == 1) { jold = p.J[i]; write = v > jold; }
+    if (write) {
+        p.J[i] = v;
+        p.Vx[i] = dir_code(e.vx); p.Vy[i] = dir_code(e.vy); p.Vz[i] = dir_code(e.vz);
+        if (p.scale_idx) p.scale_idx[i] = (uint8_t)p.scale;
+        if (p.dir) { p.dir[i] = e.vx; p.dir[p.voxels + i] = e.vy; p.dir[2 * p.voxels + i] = e.vz; }
+        return v;
     }
-};
+    return jold;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(HessTile::NT, 2)
@@ -572,40 +596,47 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
     const int by = bid % p.nty;
     const int bz = bid / p.nty;
     const int x0 = bx * T::TX - 2, y0 = by * T::TY - 2;       // global coordinates of tile entry (0, 0)
-    const int zs = p.z_begin + bz * p.zchunk;                  // first centre plane
-    const int ze = min(zs + p.zchunk, p.z_begin + p.nz);       // one past the last
     const int w = p.f.w, h = p.f.h, l = p.f.l;
+    // centre planes of this CTA, clipped to the interior 2 .. l-3
+    const int zs = max(p.z_begin + bz * p.zchunk, 2);
+    const int ze = min(min(p.z_begin + (bz + 1) * p.zchunk, p.z_begin + p.nz), l - 2);
+    if (zs >= ze) return;
 
-    // staging map: this thread's k-th tile entry and its clamped global offset (plane-independent)
-    int s_off[T::LOADS];
-    long long g_off[T::LOADS];
+    // staging map: this thread's k-th tile entry and its (clamped) global offset, plane-independent
+    int g_off[T::LOADS];
 #pragma unroll
     for (int k = 0; k < T::LOADS; ++k) {
         const int e = tid + k * T::NT;
         const int r = e / T::PW, c = e - r * T::PW;
-        s_off[k] = e < T::PLANE ? e : -1;
-        g_off[k] = (long long)clampi(y0 + r, 0, h - 1) * p.f.fpitch + clampi(x0 + c, 0, w - 1);
+        g_off[k] = clampi(y0 + r, 0, h - 1) * p.f.fpitch + clampi(x0 + c, 0, w - 1);
     }
+    constexpr int LAST_FULL = T::PLANE / T::NT;               // entries k < LAST_FULL exist for every thread
+    const bool tail = tid + LAST_FULL * T::NT < T::PLANE;
     float stage[T::LOADS];
     auto fetch = [&](int plane) {
-        const int zc = clampi(clampi(plane, 0, l - 1) - p.f.base, 0, p.f.count - 1);
-        const float* __restrict__ src = p.f.F + (long long)zc * p.f.fplane;
+        const float* __restrict__ src = p.f.F + (long long)(plane - p.f.base) * p.f.fplane;
 #pragma unroll
         for (int k = 0; k < T::LOADS; ++k)
-            if (s_off[k] >= 0) stage[k] = __ldg(src + g_off[k]);
+            if (k < LAST_FULL || tail) stage[k] = __ldg(src + g_off[k]);
     };
     auto park = [&](int plane) {
-        float* dst = ring + ((plane + T::SLOTS) % T::SLOTS) * T::PLANE;
+        float* dst = ring + (plane % T::SLOTS) * T::PLANE + tid;
 #pragma unroll
         for (int k = 0; k < T::LOADS; ++k)
-            if (s_off[k] >= 0) dst[s_off[k]] = stage[k];
+            if (k < LAST_FULL || tail) dst[k * T::NT] = stage[k];
     };
 
-    // prologue: planes zs-2 .. zs+1 into the ring, zs+2 in flight
+    // prologue: planes zs-2 .. zs+1 into the ring, zs+2 in flight (all inside the volume)
     for (int q = zs - 2; q <= zs + 1; ++q) { fetch(q); park(q); }
     fetch(zs + 2);
 
     const int xq = bx * T::TX + 4 * tx;          // first of this thread's 4 x voxels
+    bool m[4];                                   // voxel is interior in x
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = xq + j >= 2 && xq + j <= w - 3;
+    const bool any_x = m[0] || m[1] || m[2] || m[3];
+    const bool all_x = m[0] && m[1] && m[2] && m[3] && p.vec_ok;
+    const float qs = 0.25f * p.k.sigma2;
     float vmin = 3.4e38f, vmax = 0.0f;
 
     for (int z = zs; z < ze; ++z) {
@@ -613,22 +644,19 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
         __syncthreads();                          // plane z+2 visible; everyone is done with plane z-3's slot
         if (z + 1 < ze) fetch(z + 3);
 
-        const float* P0 = ring + ((z + T::SLOTS) % T::SLOTS) * T::PLANE;
-        const float* Pm1 = ring + ((z - 1 + T::SLOTS) % T::SLOTS) * T::PLANE;
-        const float* Pp1 = ring + ((z + 1 + T::SLOTS) % T::SLOTS) * T::PLANE;
-        const float* Pm2 = ring + ((z - 2 + T::SLOTS) % T::SLOTS) * T::PLANE;
-        const float* Pp2 = ring + ((z + 2 + T::SLOTS) % T::SLOTS) * T::PLANE;
-        const bool z_in = z >= 2 && z <= l - 3;
-        const float qs = 0.25f * p.k.sigma2;
+        const float* P0 = ring + (z % T::SLOTS) * T::PLANE;
+        const float* Pm1 = ring + ((z - 1) % T::SLOTS) * T::PLANE;
+        const float* Pp1 = ring + ((z + 1) % T::SLOTS) * T::PLANE;
+        const float* Pm2 = ring + ((z - 2) % T::SLOTS) * T::PLANE;
+        const float* Pp2 = ring + ((z + 2) % T::SLOTS) * T::PLANE;
 
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             const int yl = ty + 8 * half;         // row inside the tile
             const int y = by * T::TY + yl;
-            if (y >= h || xq >= w) continue;
+            if (y < 2 || y > h - 3 || !any_x) continue;
             Hess H[4];
-            const bool interior = z_in && y >= 2 && y <= h - 3 && xq >= 2 && xq + 3 <= w - 3;
-            if (interior) {
+            {
                 const int o = (yl + 2) * T::PW + 4 * tx;      // tile entry of (x = xq - 2, y)
                 // plane z: rows y-1, y, y+1 over x-2 .. x+5; rows y-2, y+2 over x .. x+3
                 float a[8], b[8], c[8];
@@ -643,27 +671,6 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
                 *reinterpret_cast<float2*>(t2 + 2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 4);
                 *reinterpret_cast<float2*>(u2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 2);
                 *reinterpret_cast<float2*>(u2 + 2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float f0 = b[j + 2];
-                    H[j].xx = __fmul_rn(__fsub_rn(__fsub_rn(b[j + 4], f0), __fsub_rn(f0, b[j])), qs);
-                    H[j].yy = __fmul_rn(__fsub_rn(__fsub_rn(u2[j], f0), __fsub_rn(f0, t2[j])), qs);
-                    H[j].xy = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 3], c[j + 1]), __fsub_rn(a[j + 3], a[j + 1])), qs);
-                }
-                // planes z-1, z+1: row y over x-1 .. x+4 (loaded as x-2 .. x+5), rows y-1, y+1 over x .. x+3
-                float m[8], n[8], mu[4], md[4], nu[4], nd[4];
-                *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(Pm1 + o);
-                *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(Pm1 + o + 4);
-                *reinterpret_cast<float4*>(n) = *reinterpret_cast<const float4*>(Pp1 + o);
-                *reinterpret_cast<float4*>(n + 4) = *reinterpret_cast<const float4*>(Pp1 + o + 4);
-                *reinterpret_cast<float2*>(mu) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 2);
-                *reinterpret_cast<float2*>(mu + 2) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 4);
-                *reinterpret_cast<float2*>(md) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 2);
-                *reinterpret_cast<float2*>(md + 2) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 4);
-                *reinterpret_cast<float2*>(nu) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 2);
-                *reinterpret_cast<float2*>(nu + 2) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 4);
-                *reinterpret_cast<float2*>(nd) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 2);
-                *reinterpret_cast<float2*>(nd + 2) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 4);
                 float k2[4], l2[4];
                 *reinterpret_cast<float2*>(k2) = *reinterpret_cast<const float2*>(Pm2 + o + 2);
                 *reinterpret_cast<float2*>(k2 + 2) = *reinterpret_cast<const float2*>(Pm2 + o + 4);
@@ -672,37 +679,53 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float f0 = b[j + 2];
-                    H[j].xz = __fmul_rn(__fsub_rn(__fsub_rn(n[j + 3], n[j + 1]), __fsub_rn(m[j + 3], m[j + 1])), qs);
-                    H[j].yz = __fmul_rn(__fsub_rn(__fsub_rn(nd[j], nu[j]), __fsub_rn(md[j], mu[j])), qs);
+                    H[j].xx = __fmul_rn(__fsub_rn(__fsub_rn(b[j + 4], f0), __fsub_rn(f0, b[j])), qs);
+                    H[j].yy = __fmul_rn(__fsub_rn(__fsub_rn(u2[j], f0), __fsub_rn(f0, t2[j])), qs);
                     H[j].zz = __fmul_rn(__fsub_rn(__fsub_rn(l2[j], f0), __fsub_rn(f0, k2[j])), qs);
+                    H[j].xy = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 3], c[j + 1]), __fsub_rn(a[j + 3], a[j + 1])), qs);
                 }
-            } else {
-                RingField rf;
-                rf.ring = ring; rf.w = w; rf.h = h; rf.l = l; rf.x0 = x0; rf.y0 = y0;
+                // planes z-1, z+1: row y over x-1 .. x+4 (loaded as x-2 .. x+5), rows y-1, y+1 over x .. x+3
+                float mm[8], nn[8], mu[4], md[4], nu[4], nd[4];
+                *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(Pm1 + o);
+                *reinterpret_cast<float4*>(mm + 4) = *reinterpret_cast<const float4*>(Pm1 + o + 4);
+                *reinterpret_cast<float4*>(nn) = *reinterpret_cast<const float4*>(Pp1 + o);
+                *reinterpret_cast<float4*>(nn + 4) = *reinterpret_cast<const float4*>(Pp1 + o + 4);
+                *reinterpret_cast<float2*>(mu) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 2);
+                *reinterpret_cast<float2*>(mu + 2) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 4);
+                *reinterpret_cast<float2*>(md) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 2);
+                *reinterpret_cast<float2*>(md + 2) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 4);
+                *reinterpret_cast<float2*>(nu) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 2);
+                *reinterpret_cast<float2*>(nu + 2) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 4);
+                *reinterpret_cast<float2*>(nd) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 2);
+                *reinterpret_cast<float2*>(nd + 2) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 4);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (xq + j < w) H[j] = hessian_at_face(rf, xq + j, y, z, p.k.sigma2);
-                    else H[j] = Hess{ 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+                for (int j = 0; j < 4; ++j) {
+                    H[j].xz = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 3], nn[j + 1]), __fsub_rn(mm[j + 3], mm[j + 1])), qs);
+                    H[j].yz = __fmul_rn(__fsub_rn(__fsub_rn(nd[j], nu[j]), __fsub_rn(md[j], mu[j])), qs);
+                }
             }
 
             const long long i0 = ((long long)(z - p.z_begin) * h + y) * w + xq;
             if (MODE == 2) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (xq + j < w) {
+                    if (m[j]) {
                         p.D[0][i0 + j] = H[j].zz; p.D[1][i0 + j] = H[j].yy; p.D[2][i0 + j] = H[j].yz;
                         p.D[3][i0 + j] = H[j].xx; p.D[4][i0 + j] = H[j].xy; p.D[5][i0 + j] = H[j].xz;
                     }
                 continue;
             }
-            const bool full = p.vec_ok && xq + 3 < w;
-            float jold[4] = { 0.f, 0.f, 0.f, 0.f };
-            if (MODE == 1) {
-                if (full) *reinterpret_cast<float4*>(jold) = *reinterpret_cast<const float4*>(p.J + i0);
-                else
+            if (!all_x) {                         // quads that straddle an x face, or an unaligned width
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (xq + j < w) jold[j] = p.J[i0 + j];
+                for (int j = 0; j < 4; ++j)
+                    if (m[j]) {
+                        const float jv = voxel_update<MODE>(p, i0 + j, H[j]);
+                        vmin = fminf(vmin, jv); vmax = fmaxf(vmax, jv);
+                    }
+                continue;
             }
+            float jold[4] = { 0.f, 0.f, 0.f, 0.f };
+            if (MODE == 1) *reinterpret_cast<float4*>(jold) = *reinterpret_cast<const float4*>(p.J + i0);
             float jn[4];
             uint8_t cx[4], cy[4], cz[4];
             float ex[4], ey[4], ez[4];
@@ -712,13 +735,13 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
                 Eig3 e;
                 eig_sym3(H[j].xx, H[j].xy, H[j].xz, H[j].yy, H[j].yz, H[j].zz, e);
                 const float v = vesselness(e, p.k);
-                wr[j] = (MODE == 0 || v > jold[j]) && (xq + j < w);
+                wr[j] = MODE == 0 || v > jold[j];
                 jn[j] = wr[j] ? v : jold[j];
                 cx[j] = dir_code(e.vx); cy[j] = dir_code(e.vy); cz[j] = dir_code(e.vz);
                 ex[j] = e.vx; ey[j] = e.vy; ez[j] = e.vz;
-                if (xq + j < w) { vmin = fminf(vmin, jn[j]); vmax = fmaxf(vmax, jn[j]); }
+                vmin = fminf(vmin, jn[j]); vmax = fmaxf(vmax, jn[j]);
             }
-            if (MODE == 0 && full) {
+            if (MODE == 0) {
                 *reinterpret_cast<float4*>(p.J + i0) = make_float4(jn[0], jn[1], jn[2], jn[3]);
                 *reinterpret_cast<uchar4*>(p.Vx + i0) = make_uchar4(cx[0], cx[1], cx[2], cx[3]);
                 *reinterpret_cast<uchar4*>(p.Vy + i0) = make_uchar4(cy[0], cy[1], cy[2], cy[3]);
@@ -729,15 +752,11 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
                     *reinterpret_cast<float4*>(p.dir + p.voxels + i0) = make_float4(ey[0], ey[1], ey[2], ey[3]);
                     *reinterpret_cast<float4*>(p.dir + 2 * p.voxels + i0) = make_float4(ez[0], ez[1], ez[2], ez[3]);
                 }
-            } else {
-                if (MODE == 1 && full) {
-                    if (wr[0] || wr[1] || wr[2] || wr[3])
-                        *reinterpret_cast<float4*>(p.J + i0) = make_float4(jn[0], jn[1], jn[2], jn[3]);
-                }
+            } else if (wr[0] || wr[1] || wr[2] || wr[3]) {
+                *reinterpret_cast<float4*>(p.J + i0) = make_float4(jn[0], jn[1], jn[2], jn[3]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (wr[j]) {
-                        if (!(MODE == 1 && full)) p.J[i0 + j] = jn[j];
                         p.Vx[i0 + j] = cx[j]; p.Vy[i0 + j] = cy[j]; p.Vz[i0 + j] = cz[j];
                         if (p.scale_idx) p.scale_idx[i0 + j] = (uint8_t)p.scale;
                         if (p.dir) {
@@ -763,6 +782,59 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
     }
 }
 
+// K3b: the shell.  Thread index -> region: z faces (whole planes), then y faces
+// (rows of the own planes), then x faces (columns of the own planes).  Edges
+// and corners are visited by more than one region, which is harmless: the
+// update is idempotent (same value on the first scale, v > J false afterwards).
+template <int MODE>
+__global__ void __launch_bounds__(128)
+hessian_eigen_shell_kernel(const __grid_constant__ VoxelParams p)
+{
+    long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+    const int w = p.f.w, h = p.f.h;
+    int x, y, z;
+    bool active = true;
+    if (t < p.n_zface) {
+        x = (int)(t % w); t /= w;
+        y = (int)(t % h);
+        z = p.zf[(int)(t / h)];
+    } else if ((t -= p.n_zface) < p.n_yface) {
+        x = (int)(t % w); t /= w;
+        y = p.yf[(int)(t % p.nyf)];
+        z = p.z_begin + (int)(t / p.nyf);
+    } else if ((t -= p.n_yface) < p.n_xface) {
+        x = p.xf[(int)(t % p.nxf)]; t /= p.nxf;
+        y = (int)(t % h);
+        z = p.z_begin + (int)(t / h);
+    } else {
+        active = false; x = y = 0; z = p.z_begin;
+    }
+    float jv = 0.0f;
+    if (active) {
+        const Hess H = hessian_at_face(p.f, x, y, z, p.k.sigma2);
+        const long long i = ((long long)(z - p.z_begin) * h + y) * w + x;
+        if (MODE == 2) {
+            p.D[0][i] = H.zz; p.D[1][i] = H.yy; p.D[2][i] = H.yz;
+            p.D[3][i] = H.xx; p.D[4][i] = H.xy; p.D[5][i] = H.xz;
+            return;
+        }
+        jv = voxel_update<MODE>(p, i, H);
+    }
+    if (MODE == 2) return;
+    if (MODE == 0) {
+        float mn = active ? jv : 3.4e38f;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+        if ((threadIdx.x & 31) == 0 && mn < 3.0e38f) atomicMin(p.minmax + 0, __float_as_int(mn));
+    }
+    if (p.last_scale) {
+        float mx = active ? jv : 0.0f;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+        if ((threadIdx.x & 31) == 0) atomicMax(p.minmax + 1, __float_as_int(mx));
+    }
+}
+
 // Stage kernel: eigen + vesselness on caller-supplied Hessians.
 __global__ void __launch_bounds__(128)
 vesselness_stage_kernel(const float* __restrict__ Dxx, const float* __restrict__ Dxy,
@@ -784,6 +856,17 @@ vesselness_stage_kernel(const float* __restrict__ Dxx, const float* __restrict__
 // K4: J -> J8 (Advantra_plugin.cpp:2499-2512, round() from :120-123).
 // minmax holds the float bit patterns of Jmin / Jmax (after the all-reduce).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t j8_code(float j, float lo, float range, bool flat)
+{
+    if (flat) return 0;
+    const float qf = __fmul_rn(__fdiv_rn(__fsub_rn(j, lo), range), 255.0f);
+    // round half away from zero (Advantra_plugin.cpp:120-123), exactly: trunc, then the exact
+    // fractional part decides (qf + 0.5f could round up across .5); negatives clamp to 0 anyway
+    int v = (int)qf;
+    v += (__fsub_rn(qf, (float)v) >= 0.5f) ? 1 : 0;
+    return (uint8_t)min(max(v, 0), 255);
+}
+
 __global__ void __launch_bounds__(256)
 j_to_j8_kernel(const float* __restrict__ J, uint8_t* __restrict__ J8, long long n, const int* __restrict__ minmax)
 {
@@ -791,17 +874,22 @@ j_to_j8_kernel(const float* __restrict__ J, uint8_t* __restrict__ J8, long long 
     const float hi = __int_as_float(minmax[1]);
     const float range = __fsub_rn(hi, lo);
     const bool flat = fabsf(range) <= 1.175494351e-38f;  // FLT_MIN
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-        int v = 0;
-        if (!flat) {
-            const float qf = __fmul_rn(__fdiv_rn(__fsub_rn(J[i], lo), range), 255.0f);
-            const double r = (double)qf;
-            v = (int)((r > 0.0) ? floor(r + 0.5) : ceil(r - 0.5));
-            v = min(max(v, 0), 255);
-        }
-        J8[i] = (uint8_t)v;
+    const long long n16 = n / 16;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n16; g += stride) {
+        const float4* src = reinterpret_cast<const float4*>(J) + 4 * g;
+        float4 q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = __ldcs(src + k);
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            o[k] = (uint32_t)j8_code(q[k].x, lo, range, flat) | ((uint32_t)j8_code(q[k].y, lo, range, flat) << 8) |
+                   ((uint32_t)j8_code(q[k].z, lo, range, flat) << 16) | ((uint32_t)j8_code(q[k].w, lo, range, flat) << 24);
+        reinterpret_cast<uint4*>(J8)[g] = make_uint4(o[0], o[1], o[2], o[3]);
     }
+    for (long long i = 16 * n16 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        J8[i] = j8_code(J[i], lo, range, flat);
 }
 
 }  // namespace frangi
