@@ -131,11 +131,15 @@ int frangi_gpu_hessian3d(const uint8_t* I_host, int w, int h, int l, float sigma
                          int device, unsigned flags);
 /* Per-voxel stage alone: eigen-decomposition + vesselness + direction of n
  * symmetric 3x3 matrices given as six float32 arrays (host).  v_out[n],
- * dir_out[3*n] planar, lambda_out[3*n] interleaved |l1|<=|l2|<=|l3| (nullable). */
+ * dir_out[3*n] planar, lambda_out[3*n] interleaved |l1|<=|l2|<=|l3| (nullable).
+ * stage_flags: 0 = the packed two-voxel path of the interior kernel,
+ * FRANGI_GPU_STAGE_SCALAR = the scalar path of the face shell. */
+enum { FRANGI_GPU_STAGE_SCALAR = 1 };
 int frangi_gpu_vesselness_stage(const float* Dxx, const float* Dxy, const float* Dxz,
                                 const float* Dyy, const float* Dyz, const float* Dzz, int64_t n,
                                 float alpha, float beta, float C, int blackwhite,
-                                float* v_out, float* dir_out, float* lambda_out, int device);
+                                float* v_out, float* dir_out, float* lambda_out, int device,
+                                unsigned stage_flags);
 
 /* ---- utilities --------------------------------------------------------------*/
 void* frangi_gpu_host_alloc(size_t bytes); /* pinned host memory (NULL on failure) */

@@ -919,7 +919,7 @@ FRANGI_API int frangi_gpu_hessian3d(const uint8_t* I_host, int w, int h, int l, 
 FRANGI_API int frangi_gpu_vesselness_stage(const float* Dxx, const float* Dxy, const float* Dxz, const float* Dyy,
                                            const float* Dyz, const float* Dzz, int64_t n, float alpha, float beta,
                                            float C, int blackwhite, float* v_out, float* dir_out,
-                                           float* lambda_out, int device)
+                                           float* lambda_out, int device, unsigned stage_flags)
 {
     if (!Dxx || !Dxy || !Dxz || !Dyy || !Dyz || !Dzz || !v_out || n < 1) return fail(FRANGI_GPU_EINVAL, "bad argument");
     RC(check_device(device));
@@ -940,8 +940,12 @@ FRANGI_API int frangi_gpu_vesselness_stage(const float* Dxx, const float* Dxy, c
         frangi_gpu tmp;
         tmp.alpha = alpha; tmp.beta = beta; tmp.C = C; tmp.blackwhite = blackwhite;
         FrangiConsts k = make_consts(&tmp, 1.0f);
-        vesselness_stage_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d[0], d[1], d[2], d[3], d[4], d[5], n, k, dv,
-                                                                      ddir, dlam);
+        if (stage_flags & FRANGI_GPU_STAGE_SCALAR)
+            vesselness_stage_scalar_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d[0], d[1], d[2], d[3], d[4], d[5], n,
+                                                                                 k, dv, ddir, dlam);
+        else
+            vesselness_stage_kernel<<<(unsigned)((n + 255) / 256), 128>>>(d[0], d[1], d[2], d[3], d[4], d[5], n, k, dv,
+                                                                          ddir, dlam);
         g_launches++;
         e = cudaGetLastError();
     }

@@ -287,6 +287,29 @@ struct Eig3 {
 
 __device__ __forceinline__ void swapf(float& a, float& b) { float t = a; a = b; b = t; }
 
+// Exactly diagonal input: the reference's QL leaves the values and the identity
+// untouched, then selection-sorts ascending (first minimum wins ties), then
+// orders by |lambda| (frangi.cpp:1473-1492, 1284-1304).
+__device__ __noinline__ Eig3 eig_diag(float a00, float a11, float a22)
+{
+    Eig3 out;
+    float e0 = a00, e1 = a11, e2 = a22;
+    int i0 = 0, i1 = 1, i2 = 2;
+    int k = 0; float pv = e0;
+    if (e1 < pv) { k = 1; pv = e1; }
+    if (e2 < pv) { k = 2; pv = e2; }
+    if (k == 1) { swapf(e0, e1); i0 = 1; i1 = 0; }
+    else if (k == 2) { swapf(e0, e2); i0 = 2; i2 = 0; }
+    if (e2 < e1) { swapf(e1, e2); int t = i1; i1 = i2; i2 = t; }
+    float m0 = fabsf(e0), m1 = fabsf(e1), m2 = fabsf(e2);
+    if (m0 >= m1 && m0 > m2) { swapf(e0, e2); swapf(m0, m2); int t = i0; i0 = i2; i2 = t; }
+    else if (m1 >= m0 && m1 > m2) { swapf(e1, e2); swapf(m1, m2); int t = i1; i1 = i2; i2 = t; }
+    if (m0 > m1) { swapf(e0, e1); int t = i0; i0 = i1; i1 = t; }
+    out.l1 = e0; out.l2 = e1; out.l3 = e2;
+    out.vx = i0 == 0 ? 1.0f : 0.0f; out.vy = i0 == 1 ? 1.0f : 0.0f; out.vz = i0 == 2 ? 1.0f : 0.0f;
+    return out;
+}
+
 // Symmetric 3x3 eigen-decomposition, float32, non-iterative, ~200 instructions.
 //  1. the eigenvalue at the isolated end of the spectrum, lam = q + sgn*p*g(|r|)
 //     with g(r) = 2 cos(acos(r)/3) from a degree-5 polynomial (|err| < 3e-6:
@@ -306,25 +329,7 @@ __device__ __forceinline__ void eig_sym3(float a00, float a01, float a02, float 
                                          float a22, Eig3& out)
 {
     const float off = a01 * a01 + a02 * a02 + a12 * a12;
-    if (off == 0.0f) {
-        // Diagonal input: the reference's QL leaves the values and the identity
-        // untouched, then selection-sorts ascending (first minimum wins ties).
-        float e0 = a00, e1 = a11, e2 = a22;
-        int i0 = 0, i1 = 1, i2 = 2;
-        int k = 0; float pv = e0;
-        if (e1 < pv) { k = 1; pv = e1; }
-        if (e2 < pv) { k = 2; pv = e2; }
-        if (k == 1) { swapf(e0, e1); i0 = 1; i1 = 0; }
-        else if (k == 2) { swapf(e0, e2); i0 = 2; i2 = 0; }
-        if (e2 < e1) { swapf(e1, e2); int t = i1; i1 = i2; i2 = t; }
-        float m0 = fabsf(e0), m1 = fabsf(e1), m2 = fabsf(e2);
-        if (m0 >= m1 && m0 > m2) { swapf(e0, e2); swapf(m0, m2); int t = i0; i0 = i2; i2 = t; }
-        else if (m1 >= m0 && m1 > m2) { swapf(e1, e2); swapf(m1, m2); int t = i1; i1 = i2; i2 = t; }
-        if (m0 > m1) { swapf(e0, e1); int t = i0; i0 = i1; i1 = t; }
-        out.l1 = e0; out.l2 = e1; out.l3 = e2;
-        out.vx = i0 == 0 ? 1.0f : 0.0f; out.vy = i0 == 1 ? 1.0f : 0.0f; out.vz = i0 == 2 ? 1.0f : 0.0f;
-        return;
-    }
+    if (off == 0.0f) { out = eig_diag(a00, a11, a22); return; }
     const float tr = a00 + a11 + a22;
     const float q = tr * (1.0f / 3.0f);
     const float b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
@@ -425,13 +430,188 @@ __device__ __forceinline__ float vesselness(const Eig3& e, const FrangiConsts& k
     return v;
 }
 
-// round((c+1)/2*255) clamped to a byte (frangi.cpp:240-250); arguments are in [-1,1]
+// ---------------------------------------------------------------------------
+// The same per-voxel stage for TWO voxels at a time in packed float32x2
+// registers: Blackwell's FMUL2 / FADD2 / FFMA2 take one issue slot for two
+// lanes (negation and |.| are operand modifiers), which matters here because
+// the stage is issue-bound, not FMA-pipe-bound.  MUFU, compares and selects
+// stay per lane.  Same algorithm as eig_sym3 / vesselness above.
+// ---------------------------------------------------------------------------
+typedef float2 P2;
+__device__ __forceinline__ P2 pbc(float s) { return make_float2(s, s); }
+__device__ __forceinline__ P2 pneg(P2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ P2 pmul(P2 a, P2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ P2 padd(P2 a, P2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ P2 psub(P2 a, P2 b) { return __fadd2_rn(a, pneg(b)); }
+__device__ __forceinline__ P2 pfma(P2 a, P2 b, P2 c) { return __ffma2_rn(a, b, c); }
+// a*b - c*d
+__device__ __forceinline__ P2 pdiff(P2 a, P2 b, P2 c, P2 d) { return __ffma2_rn(a, b, pneg(__fmul2_rn(c, d))); }
+__device__ __forceinline__ P2 prsqrt(P2 a) { return make_float2(rsqrtf(a.x), rsqrtf(a.y)); }
+
+struct Eig3x2 {
+    P2 l1, l2, l3;
+    P2 vx, vy, vz;
+};
+
+// per-lane pieces of eig_sym3
+__device__ __forceinline__ void eig_pick_column(float c00, float c11, float c22, float c01, float c02, float c12,
+                                                float& nx, float& ny, float& nz)
+{
+    const float d0 = fabsf(c00), d1 = fabsf(c11), d2 = fabsf(c22);
+    const bool s1 = d1 > d0 && d1 >= d2;
+    const bool s2 = d2 > d0 && d2 > d1;
+    nx = s2 ? c02 : (s1 ? c01 : c00);
+    ny = s2 ? c12 : (s1 ? c11 : c01);
+    nz = s2 ? c22 : (s1 ? c12 : c02);
+}
+
+// ascending triple -> |lambda| order (frangi.cpp:1284-1304) and the in-plane coordinates of the
+// eigenvector of l1 when it is not the isolated one (sel_i: column 0 is the isolated eigenvector)
+__device__ __forceinline__ void eig_order(bool top, float la, float lb, float li, float m00, float m11, float m01,
+                                          float& l1, float& l2, float& l3, bool& sel_i, float& xa0, float& xa1)
+{
+    float e0 = top ? la : li, e1 = top ? lb : la, e2 = top ? li : lb;
+    int w0 = top ? 1 : 0, w1 = top ? 2 : 1, w2 = top ? 0 : 2;
+    float m0 = fabsf(e0), m1 = fabsf(e1), m2 = fabsf(e2);
+    if (m0 >= m1 && m0 > m2) { swapf(e0, e2); swapf(m0, m2); const int t = w0; w0 = w2; w2 = t; }
+    else if (m1 >= m0 && m1 > m2) { swapf(e1, e2); swapf(m1, m2); const int t = w1; w1 = w2; w2 = t; }
+    if (m0 > m1) { swapf(e0, e1); const int t = w0; w0 = w1; w1 = t; }
+    l1 = e0; l2 = e1; l3 = e2;
+    sel_i = w0 == 0;
+    const float f0 = m00 - e0, f1 = m11 - e0;
+    const bool r0 = fabsf(f0) >= fabsf(f1);
+    const float y0 = r0 ? -m01 : f1;
+    const float y1 = r0 ? f0 : -m01;
+    const float nrm = y0 * y0 + y1 * y1;
+    const float sn = rsqrtf(nrm);
+    xa0 = nrm > 0.0f ? y0 * sn : 1.0f;
+    xa1 = nrm > 0.0f ? y1 * sn : 0.0f;
+}
+
+__device__ __forceinline__ void eig_sym3_x2(P2 a00, P2 a01, P2 a02, P2 a11, P2 a12, P2 a22, Eig3x2& out)
+{
+    const P2 off = pfma(a01, a01, pfma(a02, a02, pmul(a12, a12)));
+    const P2 tr = padd(padd(a00, a11), a22);
+    const P2 q = pmul(tr, pbc(1.0f / 3.0f));
+    const P2 b00 = psub(a00, q), b11 = psub(a11, q), b22 = psub(a22, q);
+    const P2 p26 = pmul(pfma(b00, b00, pfma(b11, b11, pfma(b22, b22, padd(off, off)))), pbc(1.0f / 6.0f));
+    const P2 ip = prsqrt(p26);
+    const P2 p = pmul(p26, ip);
+    const P2 det = pfma(b00, pdiff(b11, b22, a12, a12),
+                        pfma(pneg(a01), pdiff(a01, b22, a12, a02), pmul(a02, pdiff(a01, a12, b11, a02))));
+    const P2 hd = pmul(det, pmul(pmul(ip, ip), pmul(ip, pbc(0.5f))));
+    const P2 ar = make_float2(fminf(fabsf(hd.x), 1.0f), fminf(fabsf(hd.y), 1.0f));
+    P2 g = pfma(ar, pbc(0.00392639779f), pbc(-0.0179447089f));
+    g = pfma(ar, g, pbc(0.0437316173f));
+    g = pfma(ar, g, pbc(-0.0949838747f));
+    g = pfma(ar, g, pbc(0.333219108f));
+    g = pfma(ar, g, pbc(1.73205338f));
+    const bool topx = hd.x >= 0.0f, topy = hd.y >= 0.0f;
+    const P2 sp = make_float2(topx ? p.x : -p.x, topy ? p.y : -p.y);
+    const P2 lam = pfma(sp, g, q);
+    const P2 r00 = psub(a00, lam), r11 = psub(a11, lam), r22 = psub(a22, lam);
+    const P2 c00 = pdiff(r11, r22, a12, a12);
+    const P2 c11 = pdiff(r00, r22, a02, a02);
+    const P2 c22 = pdiff(r00, r11, a01, a01);
+    const P2 c01 = pdiff(a02, a12, a01, r22);
+    const P2 c02 = pdiff(a01, a12, a02, r11);
+    const P2 c12 = pdiff(a01, a02, a12, r00);
+    P2 nx, ny, nz;
+    eig_pick_column(c00.x, c11.x, c22.x, c01.x, c02.x, c12.x, nx.x, ny.x, nz.x);
+    eig_pick_column(c00.y, c11.y, c22.y, c01.y, c02.y, c12.y, nx.y, ny.y, nz.y);
+    const P2 inn = prsqrt(pfma(nx, nx, pfma(ny, ny, pmul(nz, nz))));
+    const P2 ix = pmul(nx, inn), iy = pmul(ny, inn), iz = pmul(nz, inn);
+    // orthonormal complement (u, w) of i
+    const bool bx = fabsf(ix.x) > fabsf(iy.x), by = fabsf(ix.y) > fabsf(iy.y);
+    const P2 ha = make_float2(bx ? ix.x : iy.x, by ? ix.y : iy.y);
+    const P2 su = prsqrt(pfma(ha, ha, pmul(iz, iz)));
+    const P2 t = pmul(iz, su), hs = pmul(ha, su);
+    const P2 ux = make_float2(bx ? -t.x : 0.0f, by ? -t.y : 0.0f);
+    const P2 uy = make_float2(bx ? 0.0f : t.x, by ? 0.0f : t.y);
+    const P2 uz = make_float2(bx ? hs.x : -hs.x, by ? hs.y : -hs.y);
+    const P2 wx = pdiff(iy, uz, iz, uy), wy = pdiff(iz, ux, ix, uz), wz = pdiff(ix, uy, iy, ux);
+    // 2x2 projection
+    const P2 aux = pfma(a00, ux, pfma(a01, uy, pmul(a02, uz)));
+    const P2 auy = pfma(a01, ux, pfma(a11, uy, pmul(a12, uz)));
+    const P2 auz = pfma(a02, ux, pfma(a12, uy, pmul(a22, uz)));
+    const P2 awx = pfma(a00, wx, pfma(a01, wy, pmul(a02, wz)));
+    const P2 awy = pfma(a01, wx, pfma(a11, wy, pmul(a12, wz)));
+    const P2 awz = pfma(a02, wx, pfma(a12, wy, pmul(a22, wz)));
+    const P2 m00 = pfma(ux, aux, pfma(uy, auy, pmul(uz, auz)));
+    const P2 m01 = pfma(wx, aux, pfma(wy, auy, pmul(wz, auz)));
+    const P2 m11 = pfma(wx, awx, pfma(wy, awy, pmul(wz, awz)));
+    const P2 sum = padd(m00, m11);
+    const P2 mean = pmul(sum, pbc(0.5f));
+    const P2 hdiff = pmul(psub(m00, m11), pbc(0.5f));
+    const P2 d2 = pfma(hdiff, hdiff, pmul(m01, m01));
+    const P2 disc = make_float2(sqrtf(d2.x), sqrtf(d2.y));
+    const P2 la = psub(mean, disc), lb = padd(mean, disc);
+    const P2 li = psub(tr, sum);         // Rayleigh-consistent isolated eigenvalue
+    bool sx, sy;
+    P2 xa0, xa1;
+    eig_order(topx, la.x, lb.x, li.x, m00.x, m11.x, m01.x, out.l1.x, out.l2.x, out.l3.x, sx, xa0.x, xa1.x);
+    eig_order(topy, la.y, lb.y, li.y, m00.y, m11.y, m01.y, out.l1.y, out.l2.y, out.l3.y, sy, xa0.y, xa1.y);
+    const P2 px = pfma(xa0, ux, pmul(xa1, wx)), py = pfma(xa0, uy, pmul(xa1, wy)), pz = pfma(xa0, uz, pmul(xa1, wz));
+    out.vx = make_float2(sx ? ix.x : px.x, sy ? ix.y : px.y);
+    out.vy = make_float2(sx ? iy.x : py.x, sy ? iy.y : py.y);
+    out.vz = make_float2(sx ? iz.x : pz.x, sy ? iz.y : pz.y);
+    // exactly diagonal inputs follow the reference's conventions (rare; see eig_sym3)
+    if (off.x == 0.0f) {
+        const Eig3 e = eig_diag(a00.x, a11.x, a22.x);
+        out.l1.x = e.l1; out.l2.x = e.l2; out.l3.x = e.l3; out.vx.x = e.vx; out.vy.x = e.vy; out.vz.x = e.vz;
+    }
+    if (off.y == 0.0f) {
+        const Eig3 e = eig_diag(a00.y, a11.y, a22.y);
+        out.l1.y = e.l1; out.l2.y = e.l2; out.l3.y = e.l3; out.vx.y = e.vx; out.vy.y = e.vy; out.vz.y = e.vz;
+    }
+}
+
+__device__ __forceinline__ P2 one_minus_exp_neg_x2(P2 x)
+{
+    P2 s = pfma(x, pbc(-1.0f / 720.0f), pbc(1.0f / 120.0f));
+    s = pfma(x, s, pbc(-1.0f / 24.0f));
+    s = pfma(x, s, pbc(1.0f / 6.0f));
+    s = pfma(x, s, pbc(-0.5f));
+    s = pfma(x, s, pbc(1.0f));
+    s = pmul(x, s);
+    const P2 xe = pmul(x, pbc(-1.4426950408889634f));
+    return make_float2(x.x < 0.25f ? s.x : 1.0f - exp2f(xe.x), x.y < 0.25f ? s.y : 1.0f - exp2f(xe.y));
+}
+
+__device__ __forceinline__ P2 vesselness_x2(const Eig3x2& e, const FrangiConsts& k)
+{
+    const P2 a1 = make_float2(fabsf(e.l1.x), fabsf(e.l1.y));
+    const P2 a2 = make_float2(fabsf(e.l2.x), fabsf(e.l2.y));
+    const P2 a3 = make_float2(fabsf(e.l3.x), fabsf(e.l3.y));
+    const P2 i3 = make_float2(__fdividef(1.0f, a3.x), __fdividef(1.0f, a3.y));
+    const P2 i2 = make_float2(__fdividef(1.0f, a2.x), __fdividef(1.0f, a2.y));
+    const P2 Ra = pmul(a2, i3);
+    const P2 a11 = pmul(a1, a1);
+    const P2 Rb2 = pmul(pmul(a11, i3), i2);
+    const P2 S2 = pfma(a2, a2, pfma(a3, a3, a11));
+    const P2 tRa = one_minus_exp_neg_x2(pmul(pmul(Ra, Ra), pbc(k.inv_2a2)));
+    const P2 xb = pmul(Rb2, pbc(-1.4426950408889634f * k.inv_2b2));
+    const P2 tRb = make_float2(exp2f(xb.x), exp2f(xb.y));
+    const P2 tS = one_minus_exp_neg_x2(pmul(S2, pbc(k.inv_2c2)));
+    P2 v = pmul(pmul(tRa, tRb), tS);
+    if (k.blackwhite) {
+        if (e.l2.x < 0.0f || e.l3.x < 0.0f) v.x = 0.0f;
+        if (e.l2.y < 0.0f || e.l3.y < 0.0f) v.y = 0.0f;
+    } else {
+        if (e.l2.x > 0.0f || e.l3.x > 0.0f) v.x = 0.0f;
+        if (e.l2.y > 0.0f || e.l3.y > 0.0f) v.y = 0.0f;
+    }
+    if (!(v.x == v.x)) v.x = 0.0f;   // NaN (0/0 on a zero Hessian) -> 0, frangi.cpp:231
+    if (!(v.y == v.y)) v.y = 0.0f;
+    return v;
+}
+
+// round((c+1)/2*255) clamped to a byte (frangi.cpp:240-250); |c| <= 1 up to rounding, so
+// (c+1)*127.5 + 0.5 lies in (0.49, 255.51) and its floor is already a byte; NaN converts to 0
 __device__ __forceinline__ uint8_t dir_code(float c)
 {
-    const float t = (c + 1.0f) * 0.5f * 255.0f;
-    int v = (int)floorf(t + 0.5f);
-    v = min(max(v, 0), 255);
-    return (uint8_t)v;
+    const int v = __float2int_rd(fmaf(c, 127.5f, 128.0f));
+    return (uint8_t)min(max(v, 0), 255);
 }
 
 // ---------------------------------------------------------------------------
@@ -529,6 +709,9 @@ struct FView {
     }
 };
 
+#ifndef HESS_MIN_CTAS
+#define HESS_MIN_CTAS 2
+#endif
 struct HessTile {
     static constexpr int TX = 128, TY = 16, NT = 256;
     static constexpr int PW = TX + 4;            // 132 floats per tile row (16-byte multiple)
@@ -565,7 +748,7 @@ struct VoxelParams {
 
 // one voxel's update (scalar stores); returns the value J holds afterwards
 template <int MODE>
-__device__ __forceinline__ float voxel_update(const VoxelParams& p, long long i, const Hess& H)
+__device__ __noinline__ float voxel_update(const VoxelParams& p, long long i, const Hess H)
 {
     Eig3 e;
     eig_sym3(H.xx, H.xy, H.xz, H.yy, H.yz, H.zz, e);
@@ -584,7 +767,7 @@ __device__ __forceinline__ float voxel_update(const VoxelParams& p, long long i,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(HessTile::NT, 2)
+__global__ void __launch_bounds__(HessTile::NT, HESS_MIN_CTAS)
 hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
 {
     using T = HessTile;
@@ -731,15 +914,21 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
             float ex[4], ey[4], ez[4];
             bool wr[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                Eig3 e;
-                eig_sym3(H[j].xx, H[j].xy, H[j].xz, H[j].yy, H[j].yz, H[j].zz, e);
-                const float v = vesselness(e, p.k);
-                wr[j] = MODE == 0 || v > jold[j];
-                jn[j] = wr[j] ? v : jold[j];
-                cx[j] = dir_code(e.vx); cy[j] = dir_code(e.vy); cz[j] = dir_code(e.vz);
-                ex[j] = e.vx; ey[j] = e.vy; ez[j] = e.vz;
-                vmin = fminf(vmin, jn[j]); vmax = fmaxf(vmax, jn[j]);
+            for (int j = 0; j < 4; j += 2) {
+                Eig3x2 e;
+                eig_sym3_x2(make_float2(H[j].xx, H[j + 1].xx), make_float2(H[j].xy, H[j + 1].xy),
+                            make_float2(H[j].xz, H[j + 1].xz), make_float2(H[j].yy, H[j + 1].yy),
+                            make_float2(H[j].yz, H[j + 1].yz), make_float2(H[j].zz, H[j + 1].zz), e);
+                const P2 v = vesselness_x2(e, p.k);
+                wr[j] = MODE == 0 || v.x > jold[j];
+                wr[j + 1] = MODE == 0 || v.y > jold[j + 1];
+                jn[j] = wr[j] ? v.x : jold[j];
+                jn[j + 1] = wr[j + 1] ? v.y : jold[j + 1];
+                cx[j] = dir_code(e.vx.x); cy[j] = dir_code(e.vy.x); cz[j] = dir_code(e.vz.x);
+                cx[j + 1] = dir_code(e.vx.y); cy[j + 1] = dir_code(e.vy.y); cz[j + 1] = dir_code(e.vz.y);
+                ex[j] = e.vx.x; ey[j] = e.vy.x; ez[j] = e.vz.x;
+                ex[j + 1] = e.vx.y; ey[j + 1] = e.vy.y; ez[j + 1] = e.vz.y;
+                vmin = fminf(vmin, fminf(jn[j], jn[j + 1])); vmax = fmaxf(vmax, fmaxf(jn[j], jn[j + 1]));
             }
             if (MODE == 0) {
                 *reinterpret_cast<float4*>(p.J + i0) = make_float4(jn[0], jn[1], jn[2], jn[3]);
@@ -842,6 +1031,39 @@ vesselness_stage_kernel(const float* __restrict__ Dxx, const float* __restrict__
                         const float* __restrict__ Dyz, const float* __restrict__ Dzz, long long n,
                         FrangiConsts k, float* __restrict__ v_out, float* __restrict__ dir_out,
                         float* __restrict__ lambda_out)
+{
+    // two matrices per thread through the packed path; an odd tail through the scalar one
+    const long long i = 2 * ((long long)blockIdx.x * 128 + threadIdx.x);
+    if (i >= n) return;
+    float v[2], ev[2][3], el[2][3];
+    if (i + 1 < n) {
+        Eig3x2 e;
+        eig_sym3_x2(make_float2(Dxx[i], Dxx[i + 1]), make_float2(Dxy[i], Dxy[i + 1]), make_float2(Dxz[i], Dxz[i + 1]),
+                    make_float2(Dyy[i], Dyy[i + 1]), make_float2(Dyz[i], Dyz[i + 1]), make_float2(Dzz[i], Dzz[i + 1]), e);
+        const P2 vv = vesselness_x2(e, k);
+        v[0] = vv.x; v[1] = vv.y;
+        ev[0][0] = e.vx.x; ev[0][1] = e.vy.x; ev[0][2] = e.vz.x; ev[1][0] = e.vx.y; ev[1][1] = e.vy.y; ev[1][2] = e.vz.y;
+        el[0][0] = e.l1.x; el[0][1] = e.l2.x; el[0][2] = e.l3.x; el[1][0] = e.l1.y; el[1][1] = e.l2.y; el[1][2] = e.l3.y;
+    } else {
+        Eig3 e;
+        eig_sym3(Dxx[i], Dxy[i], Dxz[i], Dyy[i], Dyz[i], Dzz[i], e);
+        v[0] = vesselness(e, k);
+        ev[0][0] = e.vx; ev[0][1] = e.vy; ev[0][2] = e.vz; el[0][0] = e.l1; el[0][1] = e.l2; el[0][2] = e.l3;
+    }
+    for (int q = 0; q < 2 && i + q < n; ++q) {
+        v_out[i + q] = v[q];
+        if (dir_out) { dir_out[i + q] = ev[q][0]; dir_out[n + i + q] = ev[q][1]; dir_out[2 * n + i + q] = ev[q][2]; }
+        if (lambda_out) { lambda_out[3 * (i + q)] = el[q][0]; lambda_out[3 * (i + q) + 1] = el[q][1]; lambda_out[3 * (i + q) + 2] = el[q][2]; }
+    }
+}
+
+// Scalar twin of the stage kernel (the path of the face shell and of ragged quads).
+__global__ void __launch_bounds__(128)
+vesselness_stage_scalar_kernel(const float* __restrict__ Dxx, const float* __restrict__ Dxy,
+                               const float* __restrict__ Dxz, const float* __restrict__ Dyy,
+                               const float* __restrict__ Dyz, const float* __restrict__ Dzz, long long n,
+                               FrangiConsts k, float* __restrict__ v_out, float* __restrict__ dir_out,
+                               float* __restrict__ lambda_out)
 {
     const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;

@@ -23,7 +23,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libfrangi_gpu.so")
+# FRANGI_GPU_LIB selects another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("FRANGI_GPU_LIB") or os.path.join(_HERE, "_lib", "libfrangi_gpu.so")
 
 FLAG_FMA_SMOOTHING = 1
 FLAG_DIR_F32 = 2
@@ -63,7 +64,7 @@ SYMBOLS = {
     "frangi_gpu_hessian3d": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                        _VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_uint]),
     "frangi_gpu_vesselness_stage": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_float, C.c_float,
-                                              C.c_float, C.c_int, _VP, _VP, _VP, C.c_int]),
+                                              C.c_float, C.c_int, _VP, _VP, _VP, C.c_int, C.c_uint]),
     "frangi_gpu_host_alloc": (_VP, [C.c_size_t]),
     "frangi_gpu_host_free": (None, [_VP]),
     "frangi_gpu_device_count": (C.c_int, []),
@@ -317,7 +318,7 @@ class Frangi:
                                                    device, self.flags & FLAG_FMA_SMOOTHING))
         return dict(zip(names, D))
 
-    def vesselness_stage(self, D, device=0, want_lambda=True):
+    def vesselness_stage(self, D, device=0, want_lambda=True, scalar=False):
         arrs = [np.ascontiguousarray(D[k], np.float32) for k in ("Dxx", "Dxy", "Dxz", "Dyy", "Dyz", "Dzz")]
         n = arrs[0].size
         v = np.empty(arrs[0].shape, np.float32)
@@ -325,7 +326,7 @@ class Frangi:
         lam = np.empty(arrs[0].shape + (3,), np.float32) if want_lambda else None
         _check(load_library().frangi_gpu_vesselness_stage(*[_ptr(a) for a in arrs], n, self.alpha, self.beta,
                                                           self.C, int(self.blackwhite), _ptr(v), _ptr(dr),
-                                                          _ptr(lam), device))
+                                                          _ptr(lam), device, 1 if scalar else 0))
         return v, dr, lam
 
     def close(self):

@@ -55,7 +55,8 @@ def test_hessian3d_bit_exact(oracle, shape, sigma):
 
 
 # ---------------------------------------------------------------- stage: eigen + vesselness
-def test_vesselness_stage_random_and_degenerate(oracle):
+@pytest.mark.parametrize("scalar", [False, True])
+def test_vesselness_stage_random_and_degenerate(oracle, scalar):
     rng = np.random.default_rng(3)
     n = 200000
     M = rng.normal(size=(n, 3, 3)).astype(np.float32) * rng.choice([1e-2, 1.0, 50.0], size=(n, 1, 1)).astype(np.float32)
@@ -72,7 +73,7 @@ def test_vesselness_stage_random_and_degenerate(oracle):
     D = dict(Dxx=A[:, 0, 0], Dxy=A[:, 0, 1], Dxz=A[:, 0, 2], Dyy=A[:, 1, 1], Dyz=A[:, 1, 2], Dzz=A[:, 2, 2])
     D = {k: np.ascontiguousarray(v) for k, v in D.items()}
     f = _frangi()
-    v, d, lam_g = f.vesselness_stage(D)
+    v, d, lam_g = f.vesselness_stage(D, scalar=scalar)
     vr, dr, lam_r = oracle.vesselness_stage(D, want_lambda=True)
     # eigenvalues: absolute error relative to the spectral norm
     scale = np.abs(lam_r).max(1)

@@ -27,9 +27,10 @@ def run(w, h, l, sigs, flags=0, reps=3, tile=None):
     p.close()
 
 if __name__ == "__main__":
-    run(256, 256, 64, [2., 4., 6.])
-    run(512, 512, 128, [2., 4., 6.])
-    run(512, 512, 128, [2., 4., 6.], flags=1)
-    run(1024, 1024, 256, [1., 2., 3., 4., 5., 6.], tile=(256, 256, 64))
-    run(2048, 2048, 512, [2., 4., 6.], tile=(512, 512, 128))
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    print("lib:", os.environ.get("FRANGI_GPU_LIB", "default"))
+    if which == "all":
+        run(256, 256, 64, [2., 4., 6.])
+        run(512, 512, 128, [2., 4., 6.], flags=1)
+        run(1024, 1024, 256, [1., 2., 3., 4., 5., 6.], tile=(256, 256, 64))
     run(2048, 2048, 512, [2., 4., 6.], flags=1, tile=(512, 512, 128))
