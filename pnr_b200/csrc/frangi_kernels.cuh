@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "frangi_voxel_math.cuh"
+
 namespace frangi {
 
 constexpr int kMaxRadius = 30;              // largest supported tap radius (sigma <= 10 in xy)
@@ -255,366 +257,6 @@ gauss_z_kernel(const __grid_constant__ ZParams p, const __grid_constant__ GaussT
 }
 
 // ---------------------------------------------------------------------------
-// Per-voxel math of K3.
-// ---------------------------------------------------------------------------
-struct FrangiConsts {
-    float inv_2a2;    // 1 / (2*alpha*alpha)   (float products as in frangi.cpp:215-217)
-    float inv_2b2;
-    float inv_2c2;
-    float sigma2;     // sigma*sigma, float    (frangi.cpp:319)
-    int blackwhite;
-};
-
-// 1 - exp(-x) for x >= 0 without cancellation (the reference evaluates it in
-// double; in float32 the subtraction would lose everything for the S term,
-// where x ~ 1e-4 with C = 500): alternating series below 1/4 (truncation
-// < 2e-6 relative), 1 - ex2 above (ex2.approx is good to 2 ulp).
-__device__ __forceinline__ float one_minus_exp_neg(float x)
-{
-    const float big = 1.0f - exp2f(-1.4426950408889634f * x);
-    float s = fmaf(x, -1.0f / 720.0f, 1.0f / 120.0f);
-    s = fmaf(x, s, -1.0f / 24.0f);
-    s = fmaf(x, s, 1.0f / 6.0f);
-    s = fmaf(x, s, -0.5f);
-    s = fmaf(x, s, 1.0f);
-    return x < 0.25f ? x * s : big;
-}
-
-struct Eig3 {
-    float l1, l2, l3;   // |l1| <= |l2| <= |l3| with the reference's tie rules
-    float vx, vy, vz;   // unit eigenvector of l1
-};
-
-__device__ __forceinline__ void swapf(float& a, float& b) { float t = a; a = b; b = t; }
-
-// Exactly diagonal input: the reference's QL leaves the values and the identity
-// untouched, then selection-sorts ascending (first minimum wins ties), then
-// orders by |lambda| (frangi.cpp:1473-1492, 1284-1304).
-__device__ __noinline__ Eig3 eig_diag(float a00, float a11, float a22)
-{
-    Eig3 out;
-    float e0 = a00, e1 = a11, e2 = a22;
-    int i0 = 0, i1 = 1, i2 = 2;
-    int k = 0; float pv = e0;
-    if (e1 < pv) { k = 1; pv = e1; }
-    if (e2 < pv) { k = 2; pv = e2; }
-    if (k == 1) { swapf(e0, e1); i0 = 1; i1 = 0; }
-    else if (k == 2) { swapf(e0, e2); i0 = 2; i2 = 0; }
-    if (e2 < e1) { swapf(e1, e2); int t = i1; i1 = i2; i2 = t; }
-    float m0 = fabsf(e0), m1 = fabsf(e1), m2 = fabsf(e2);
-    if (m0 >= m1 && m0 > m2) { swapf(e0, e2); swapf(m0, m2); int t = i0; i0 = i2; i2 = t; }
-    else if (m1 >= m0 && m1 > m2) { swapf(e1, e2); swapf(m1, m2); int t = i1; i1 = i2; i2 = t; }
-    if (m0 > m1) { swapf(e0, e1); int t = i0; i0 = i1; i1 = t; }
-    out.l1 = e0; out.l2 = e1; out.l3 = e2;
-    out.vx = i0 == 0 ? 1.0f : 0.0f; out.vy = i0 == 1 ? 1.0f : 0.0f; out.vz = i0 == 2 ? 1.0f : 0.0f;
-    return out;
-}
-
-// Symmetric 3x3 eigen-decomposition, float32, non-iterative, ~200 instructions.
-//  1. the eigenvalue at the isolated end of the spectrum, lam = q + sgn*p*g(|r|)
-//     with g(r) = 2 cos(acos(r)/3) from a degree-5 polynomial (|err| < 3e-6:
-//     lam only has to be good enough to pick out its eigenvector, see 3);
-//  2. its eigenvector i = the largest column of adj(A - lam I) (all columns are
-//     multiples of it; the largest diagonal entry of the adjugate picks the
-//     best conditioned one);
-//  3. the other two eigenvalues from the 2x2 projection M of A on the orthogonal
-//     complement of i -- their split is sqrt(hdiff^2 + m01^2), a sum of squares,
-//     so a close pair (the tube case l2 ~ l3) is resolved to float accuracy --
-//     and the isolated eigenvalue as trace(A) - trace(M), which is second-order
-//     accurate in the error of i;
-//  4. |lambda| ordering with the reference's tie rules (frangi.cpp:1284-1304),
-//     tracking only WHICH eigenvector ends up in column 0; it is then built once.
-// Replaces eigen_decomposition (frangi.cpp:1269-1306) semantically.
-__device__ __forceinline__ void eig_sym3(float a00, float a01, float a02, float a11, float a12,
-                                         float a22, Eig3& out)
-{
-    const float off = a01 * a01 + a02 * a02 + a12 * a12;
-    if (off == 0.0f) { out = eig_diag(a00, a11, a22); return; }
-    const float tr = a00 + a11 + a22;
-    const float q = tr * (1.0f / 3.0f);
-    const float b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
-    const float p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0f * off;
-    const float ip = rsqrtf(p2 * (1.0f / 6.0f));
-    const float p = p2 * (1.0f / 6.0f) * ip;
-    const float det = b00 * (b11 * b22 - a12 * a12) - a01 * (a01 * b22 - a12 * a02) + a02 * (a01 * a12 - b11 * a02);
-    const float hd = 0.5f * det * ip * ip * ip;
-    const bool top = hd >= 0.0f;          // the largest eigenvalue is the isolated one
-    const float ar = fminf(fabsf(hd), 1.0f);
-    float g = fmaf(ar, 0.00392639779f, -0.0179447089f);
-    g = fmaf(ar, g, 0.0437316173f);
-    g = fmaf(ar, g, -0.0949838747f);
-    g = fmaf(ar, g, 0.333219108f);
-    g = fmaf(ar, g, 1.73205338f);
-    const float lam = top ? fmaf(p, g, q) : fmaf(-p, g, q);
-    // adj(A - lam I): every column is a multiple of the eigenvector
-    const float r00 = a00 - lam, r11 = a11 - lam, r22 = a22 - lam;
-    const float c00 = r11 * r22 - a12 * a12;
-    const float c11 = r00 * r22 - a02 * a02;
-    const float c22 = r00 * r11 - a01 * a01;
-    const float c01 = a02 * a12 - a01 * r22;
-    const float c02 = a01 * a12 - a02 * r11;
-    const float c12 = a01 * a02 - a12 * r00;
-    const float d0 = fabsf(c00), d1 = fabsf(c11), d2 = fabsf(c22);
-    float nx = c00, ny = c01, nz = c02;
-    if (d1 > d0 && d1 >= d2) { nx = c01; ny = c11; nz = c12; }
-    if (d2 > d0 && d2 > d1) { nx = c02; ny = c12; nz = c22; }
-    const float inn = rsqrtf(nx * nx + ny * ny + nz * nz);
-    const float ix = nx * inn, iy = ny * inn, iz = nz * inn;
-    // orthonormal complement (u, w) of i
-    const bool xbig = fabsf(ix) > fabsf(iy);
-    const float ha = xbig ? ix : iy;
-    const float su = rsqrtf(ha * ha + iz * iz);
-    const float ux = xbig ? -iz * su : 0.0f;
-    const float uy = xbig ? 0.0f : iz * su;
-    const float uz = xbig ? ix * su : -iy * su;
-    const float wx = iy * uz - iz * uy, wy = iz * ux - ix * uz, wz = ix * uy - iy * ux;
-    // 2x2 projection
-    const float aux = a00 * ux + a01 * uy + a02 * uz;
-    const float auy = a01 * ux + a11 * uy + a12 * uz;
-    const float auz = a02 * ux + a12 * uy + a22 * uz;
-    const float awx = a00 * wx + a01 * wy + a02 * wz;
-    const float awy = a01 * wx + a11 * wy + a12 * wz;
-    const float awz = a02 * wx + a12 * wy + a22 * wz;
-    const float m00 = ux * aux + uy * auy + uz * auz;
-    const float m01 = wx * aux + wy * auy + wz * auz;
-    const float m11 = wx * awx + wy * awy + wz * awz;
-    const float mean = 0.5f * (m00 + m11);
-    const float hdiff = 0.5f * (m00 - m11);
-    const float disc = sqrtf(hdiff * hdiff + m01 * m01);
-    const float la = mean - disc, lb = mean + disc;
-    const float li = tr - (m00 + m11);   // Rayleigh-consistent isolated eigenvalue
-    // ascending triple and which vector belongs to each: 0 = i, 1 = in-plane of la, 2 = in-plane of lb
-    float e0 = top ? la : li, e1 = top ? lb : la, e2 = top ? li : lb;
-    int w0 = top ? 1 : 0, w1 = top ? 2 : 1, w2 = top ? 0 : 2;
-    // re-order by absolute value with the reference's rules (frangi.cpp:1284-1304)
-    float m0 = fabsf(e0), m1 = fabsf(e1), m2 = fabsf(e2);
-    if (m0 >= m1 && m0 > m2) { swapf(e0, e2); swapf(m0, m2); const int t = w0; w0 = w2; w2 = t; }
-    else if (m1 >= m0 && m1 > m2) { swapf(e1, e2); swapf(m1, m2); const int t = w1; w1 = w2; w2 = t; }
-    if (m0 > m1) { swapf(e0, e1); const int t = w0; w0 = w1; w1 = t; }
-    out.l1 = e0; out.l2 = e1; out.l3 = e2;
-    // eigenvector of e0: i itself, or the null vector of (M - e0 I) inside span(u, w)
-    const float f0 = m00 - e0, f1 = m11 - e0;
-    const bool r0 = fabsf(f0) >= fabsf(f1);
-    float xa0 = r0 ? -m01 : f1;
-    float xa1 = r0 ? f0 : -m01;
-    const float nrm = xa0 * xa0 + xa1 * xa1;
-    const float sn = rsqrtf(nrm);
-    xa0 = nrm > 0.0f ? xa0 * sn : 1.0f;
-    xa1 = nrm > 0.0f ? xa1 * sn : 0.0f;
-    const float px = xa0 * ux + xa1 * wx, py = xa0 * uy + xa1 * wy, pz = xa0 * uz + xa1 * wz;
-    out.vx = w0 == 0 ? ix : px;
-    out.vy = w0 == 0 ? iy : py;
-    out.vz = w0 == 0 ? iz : pz;
-}
-
-// Frangi vesselness from |lambda|-sorted eigenvalues (frangi.cpp:206-231).
-__device__ __forceinline__ float vesselness(const Eig3& e, const FrangiConsts& k)
-{
-    const float a1 = fabsf(e.l1), a2 = fabsf(e.l2), a3 = fabsf(e.l3);
-    const float i3 = __fdividef(1.0f, a3);
-    const float Ra = a2 * i3;
-    const float Rb2 = a1 * a1 * i3 * __fdividef(1.0f, a2);    // (|l1| / sqrt(|l2 l3|))^2
-    const float S2 = a1 * a1 + a2 * a2 + a3 * a3;
-    const float tRa = one_minus_exp_neg(Ra * Ra * k.inv_2a2);
-    const float tRb = exp2f(-1.4426950408889634f * Rb2 * k.inv_2b2);
-    const float tS = one_minus_exp_neg(S2 * k.inv_2c2);
-    float v = tRa * tRb * tS;
-    if (k.blackwhite) {
-        if (e.l2 < 0.0f) v = 0.0f;
-        if (e.l3 < 0.0f) v = 0.0f;
-    } else {
-        if (e.l2 > 0.0f) v = 0.0f;
-        if (e.l3 > 0.0f) v = 0.0f;
-    }
-    if (!(v == v)) v = 0.0f;  // NaN (0/0 on a zero Hessian) -> 0, frangi.cpp:231
-    return v;
-}
-
-// ---------------------------------------------------------------------------
-// The same per-voxel stage for TWO voxels at a time in packed float32x2
-// registers: Blackwell's FMUL2 / FADD2 / FFMA2 take one issue slot for two
-// lanes (negation and |.| are operand modifiers), which matters here because
-// the stage is issue-bound, not FMA-pipe-bound.  MUFU, compares and selects
-// stay per lane.  Same algorithm as eig_sym3 / vesselness above.
-// ---------------------------------------------------------------------------
-typedef float2 P2;
-__device__ __forceinline__ P2 pbc(float s) { return make_float2(s, s); }
-__device__ __forceinline__ P2 pneg(P2 a) { return make_float2(-a.x, -a.y); }
-__device__ __forceinline__ P2 pmul(P2 a, P2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ P2 padd(P2 a, P2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ P2 psub(P2 a, P2 b) { return __fadd2_rn(a, pneg(b)); }
-__device__ __forceinline__ P2 pfma(P2 a, P2 b, P2 c) { return __ffma2_rn(a, b, c); }
-// a*b - c*d
-__device__ __forceinline__ P2 pdiff(P2 a, P2 b, P2 c, P2 d) { return __ffma2_rn(a, b, pneg(__fmul2_rn(c, d))); }
-__device__ __forceinline__ P2 prsqrt(P2 a) { return make_float2(rsqrtf(a.x), rsqrtf(a.y)); }
-
-struct Eig3x2 {
-    P2 l1, l2, l3;
-    P2 vx, vy, vz;
-};
-
-// per-lane pieces of eig_sym3
-__device__ __forceinline__ void eig_pick_column(float c00, float c11, float c22, float c01, float c02, float c12,
-                                                float& nx, float& ny, float& nz)
-{
-    const float d0 = fabsf(c00), d1 = fabsf(c11), d2 = fabsf(c22);
-    const bool s1 = d1 > d0 && d1 >= d2;
-    const bool s2 = d2 > d0 && d2 > d1;
-    nx = s2 ? c02 : (s1 ? c01 : c00);
-    ny = s2 ? c12 : (s1 ? c11 : c01);
-    nz = s2 ? c22 : (s1 ? c12 : c02);
-}
-
-// ascending triple -> |lambda| order (frangi.cpp:1284-1304) and the in-plane coordinates of the
-// eigenvector of l1 when it is not the isolated one (sel_i: column 0 is the isolated eigenvector)
-__device__ __forceinline__ void eig_order(bool top, float la, float lb, float li, float m00, float m11, float m01,
-                                          float& l1, float& l2, float& l3, bool& sel_i, float& xa0, float& xa1)
-{
-    float e0 = top ? la : li, e1 = top ? lb : la, e2 = top ? li : lb;
-    int w0 = top ? 1 : 0, w1 = top ? 2 : 1, w2 = top ? 0 : 2;
-    float m0 = fabsf(e0), m1 = fabsf(e1), m2 = fabsf(e2);
-    if (m0 >= m1 && m0 > m2) { swapf(e0, e2); swapf(m0, m2); const int t = w0; w0 = w2; w2 = t; }
-    else if (m1 >= m0 && m1 > m2) { swapf(e1, e2); swapf(m1, m2); const int t = w1; w1 = w2; w2 = t; }
-    if (m0 > m1) { swapf(e0, e1); const int t = w0; w0 = w1; w1 = t; }
-    l1 = e0; l2 = e1; l3 = e2;
-    sel_i = w0 == 0;
-    const float f0 = m00 - e0, f1 = m11 - e0;
-    const bool r0 = fabsf(f0) >= fabsf(f1);
-    const float y0 = r0 ? -m01 : f1;
-    const float y1 = r0 ? f0 : -m01;
-    const float nrm = y0 * y0 + y1 * y1;
-    const float sn = rsqrtf(nrm);
-    xa0 = nrm > 0.0f ? y0 * sn : 1.0f;
-    xa1 = nrm > 0.0f ? y1 * sn : 0.0f;
-}
-
-__device__ __forceinline__ void eig_sym3_x2(P2 a00, P2 a01, P2 a02, P2 a11, P2 a12, P2 a22, Eig3x2& out)
-{
-    const P2 off = pfma(a01, a01, pfma(a02, a02, pmul(a12, a12)));
-    const P2 tr = padd(padd(a00, a11), a22);
-    const P2 q = pmul(tr, pbc(1.0f / 3.0f));
-    const P2 b00 = psub(a00, q), b11 = psub(a11, q), b22 = psub(a22, q);
-    const P2 p26 = pmul(pfma(b00, b00, pfma(b11, b11, pfma(b22, b22, padd(off, off)))), pbc(1.0f / 6.0f));
-    const P2 ip = prsqrt(p26);
-    const P2 p = pmul(p26, ip);
-    const P2 det = pfma(b00, pdiff(b11, b22, a12, a12),
-                        pfma(pneg(a01), pdiff(a01, b22, a12, a02), pmul(a02, pdiff(a01, a12, b11, a02))));
-    const P2 hd = pmul(det, pmul(pmul(ip, ip), pmul(ip, pbc(0.5f))));
-    const P2 ar = make_float2(fminf(fabsf(hd.x), 1.0f), fminf(fabsf(hd.y), 1.0f));
-    P2 g = pfma(ar, pbc(0.00392639779f), pbc(-0.0179447089f));
-    g = pfma(ar, g, pbc(0.0437316173f));
-    g = pfma(ar, g, pbc(-0.0949838747f));
-    g = pfma(ar, g, pbc(0.333219108f));
-    g = pfma(ar, g, pbc(1.73205338f));
-    const bool topx = hd.x >= 0.0f, topy = hd.y >= 0.0f;
-    const P2 sp = make_float2(topx ? p.x : -p.x, topy ? p.y : -p.y);
-    const P2 lam = pfma(sp, g, q);
-    const P2 r00 = psub(a00, lam), r11 = psub(a11, lam), r22 = psub(a22, lam);
-    const P2 c00 = pdiff(r11, r22, a12, a12);
-    const P2 c11 = pdiff(r00, r22, a02, a02);
-    const P2 c22 = pdiff(r00, r11, a01, a01);
-    const P2 c01 = pdiff(a02, a12, a01, r22);
-    const P2 c02 = pdiff(a01, a12, a02, r11);
-    const P2 c12 = pdiff(a01, a02, a12, r00);
-    P2 nx, ny, nz;
-    eig_pick_column(c00.x, c11.x, c22.x, c01.x, c02.x, c12.x, nx.x, ny.x, nz.x);
-    eig_pick_column(c00.y, c11.y, c22.y, c01.y, c02.y, c12.y, nx.y, ny.y, nz.y);
-    const P2 inn = prsqrt(pfma(nx, nx, pfma(ny, ny, pmul(nz, nz))));
-    const P2 ix = pmul(nx, inn), iy = pmul(ny, inn), iz = pmul(nz, inn);
-    // orthonormal complement (u, w) of i
-    const bool bx = fabsf(ix.x) > fabsf(iy.x), by = fabsf(ix.y) > fabsf(iy.y);
-    const P2 ha = make_float2(bx ? ix.x : iy.x, by ? ix.y : iy.y);
-    const P2 su = prsqrt(pfma(ha, ha, pmul(iz, iz)));
-    const P2 t = pmul(iz, su), hs = pmul(ha, su);
-    const P2 ux = make_float2(bx ? -t.x : 0.0f, by ? -t.y : 0.0f);
-    const P2 uy = make_float2(bx ? 0.0f : t.x, by ? 0.0f : t.y);
-    const P2 uz = make_float2(bx ? hs.x : -hs.x, by ? hs.y : -hs.y);
-    const P2 wx = pdiff(iy, uz, iz, uy), wy = pdiff(iz, ux, ix, uz), wz = pdiff(ix, uy, iy, ux);
-    // 2x2 projection
-    const P2 aux = pfma(a00, ux, pfma(a01, uy, pmul(a02, uz)));
-    const P2 auy = pfma(a01, ux, pfma(a11, uy, pmul(a12, uz)));
-    const P2 auz = pfma(a02, ux, pfma(a12, uy, pmul(a22, uz)));
-    const P2 awx = pfma(a00, wx, pfma(a01, wy, pmul(a02, wz)));
-    const P2 awy = pfma(a01, wx, pfma(a11, wy, pmul(a12, wz)));
-    const P2 awz = pfma(a02, wx, pfma(a12, wy, pmul(a22, wz)));
-    const P2 m00 = pfma(ux, aux, pfma(uy, auy, pmul(uz, auz)));
-    const P2 m01 = pfma(wx, aux, pfma(wy, auy, pmul(wz, auz)));
-    const P2 m11 = pfma(wx, awx, pfma(wy, awy, pmul(wz, awz)));
-    const P2 sum = padd(m00, m11);
-    const P2 mean = pmul(sum, pbc(0.5f));
-    const P2 hdiff = pmul(psub(m00, m11), pbc(0.5f));
-    const P2 d2 = pfma(hdiff, hdiff, pmul(m01, m01));
-    const P2 disc = make_float2(sqrtf(d2.x), sqrtf(d2.y));
-    const P2 la = psub(mean, disc), lb = padd(mean, disc);
-    const P2 li = psub(tr, sum);         // Rayleigh-consistent isolated eigenvalue
-    bool sx, sy;
-    P2 xa0, xa1;
-    eig_order(topx, la.x, lb.x, li.x, m00.x, m11.x, m01.x, out.l1.x, out.l2.x, out.l3.x, sx, xa0.x, xa1.x);
-    eig_order(topy, la.y, lb.y, li.y, m00.y, m11.y, m01.y, out.l1.y, out.l2.y, out.l3.y, sy, xa0.y, xa1.y);
-    const P2 px = pfma(xa0, ux, pmul(xa1, wx)), py = pfma(xa0, uy, pmul(xa1, wy)), pz = pfma(xa0, uz, pmul(xa1, wz));
-    out.vx = make_float2(sx ? ix.x : px.x, sy ? ix.y : px.y);
-    out.vy = make_float2(sx ? iy.x : py.x, sy ? iy.y : py.y);
-    out.vz = make_float2(sx ? iz.x : pz.x, sy ? iz.y : pz.y);
-    // exactly diagonal inputs follow the reference's conventions (rare; see eig_sym3)
-    if (off.x == 0.0f) {
-        const Eig3 e = eig_diag(a00.x, a11.x, a22.x);
-        out.l1.x = e.l1; out.l2.x = e.l2; out.l3.x = e.l3; out.vx.x = e.vx; out.vy.x = e.vy; out.vz.x = e.vz;
-    }
-    if (off.y == 0.0f) {
-        const Eig3 e = eig_diag(a00.y, a11.y, a22.y);
-        out.l1.y = e.l1; out.l2.y = e.l2; out.l3.y = e.l3; out.vx.y = e.vx; out.vy.y = e.vy; out.vz.y = e.vz;
-    }
-}
-
-__device__ __forceinline__ P2 one_minus_exp_neg_x2(P2 x)
-{
-    P2 s = pfma(x, pbc(-1.0f / 720.0f), pbc(1.0f / 120.0f));
-    s = pfma(x, s, pbc(-1.0f / 24.0f));
-    s = pfma(x, s, pbc(1.0f / 6.0f));
-    s = pfma(x, s, pbc(-0.5f));
-    s = pfma(x, s, pbc(1.0f));
-    s = pmul(x, s);
-    const P2 xe = pmul(x, pbc(-1.4426950408889634f));
-    return make_float2(x.x < 0.25f ? s.x : 1.0f - exp2f(xe.x), x.y < 0.25f ? s.y : 1.0f - exp2f(xe.y));
-}
-
-__device__ __forceinline__ P2 vesselness_x2(const Eig3x2& e, const FrangiConsts& k)
-{
-    const P2 a1 = make_float2(fabsf(e.l1.x), fabsf(e.l1.y));
-    const P2 a2 = make_float2(fabsf(e.l2.x), fabsf(e.l2.y));
-    const P2 a3 = make_float2(fabsf(e.l3.x), fabsf(e.l3.y));
-    const P2 i3 = make_float2(__fdividef(1.0f, a3.x), __fdividef(1.0f, a3.y));
-    const P2 i2 = make_float2(__fdividef(1.0f, a2.x), __fdividef(1.0f, a2.y));
-    const P2 Ra = pmul(a2, i3);
-    const P2 a11 = pmul(a1, a1);
-    const P2 Rb2 = pmul(pmul(a11, i3), i2);
-    const P2 S2 = pfma(a2, a2, pfma(a3, a3, a11));
-    const P2 tRa = one_minus_exp_neg_x2(pmul(pmul(Ra, Ra), pbc(k.inv_2a2)));
-    const P2 xb = pmul(Rb2, pbc(-1.4426950408889634f * k.inv_2b2));
-    const P2 tRb = make_float2(exp2f(xb.x), exp2f(xb.y));
-    const P2 tS = one_minus_exp_neg_x2(pmul(S2, pbc(k.inv_2c2)));
-    P2 v = pmul(pmul(tRa, tRb), tS);
-    if (k.blackwhite) {
-        if (e.l2.x < 0.0f || e.l3.x < 0.0f) v.x = 0.0f;
-        if (e.l2.y < 0.0f || e.l3.y < 0.0f) v.y = 0.0f;
-    } else {
-        if (e.l2.x > 0.0f || e.l3.x > 0.0f) v.x = 0.0f;
-        if (e.l2.y > 0.0f || e.l3.y > 0.0f) v.y = 0.0f;
-    }
-    if (!(v.x == v.x)) v.x = 0.0f;   // NaN (0/0 on a zero Hessian) -> 0, frangi.cpp:231
-    if (!(v.y == v.y)) v.y = 0.0f;
-    return v;
-}
-
-// round((c+1)/2*255) clamped to a byte (frangi.cpp:240-250); |c| <= 1 up to rounding, so
-// (c+1)*127.5 + 0.5 lies in (0.49, 255.51) and its floor is already a byte; NaN converts to 0
-__device__ __forceinline__ uint8_t dir_code(float c)
-{
-    const int v = __float2int_rd(fmaf(c, 127.5f, 128.0f));
-    return (uint8_t)min(max(v, 0), 255);
-}
-
-// ---------------------------------------------------------------------------
 // Second differences with the reference's face rules (frangi.cpp:306-381):
 // first difference along an axis = s * (f[hi] - f[lo]) with lo = max(c-1,0),
 // hi = min(c+1,n-1), s = 1 on a face and 0.5 inside; the second difference
@@ -751,14 +393,14 @@ template <int MODE>
 __device__ __noinline__ float voxel_update(const VoxelParams& p, long long i, const Hess H)
 {
     Eig3 e;
-    eig_sym3(H.xx, H.xy, H.xz, H.yy, H.yz, H.zz, e);
-    const float v = vesselness(e, p.k);
+    eig_sym3<float>(H.xx, H.xy, H.xz, H.yy, H.yz, H.zz, e);
+    const float v = vesselness<float>(e, p.k);
     float jold = 0.0f;
     bool write = MODE == 0;
     if (MODE == 1) { jold = p.J[i]; write = v > jold; }
     if (write) {
         p.J[i] = v;
-        p.Vx[i] = dir_code(e.vx); p.Vy[i] = dir_code(e.vy); p.Vz[i] = dir_code(e.vz);
+        p.Vx[i] = (uint8_t)dir_code(e.vx); p.Vy[i] = (uint8_t)dir_code(e.vy); p.Vz[i] = (uint8_t)dir_code(e.vz);
         if (p.scale_idx) p.scale_idx[i] = (uint8_t)p.scale;
         if (p.dir) { p.dir[i] = e.vx; p.dir[p.voxels + i] = e.vy; p.dir[2 * p.voxels + i] = e.vz; }
         return v;
@@ -838,7 +480,8 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
             const int yl = ty + 8 * half;         // row inside the tile
             const int y = by * T::TY + yl;
             if (y < 2 || y > h - 3 || !any_x) continue;
-            Hess H[4];
+            // second differences of the quad as two packed pairs (voxels 0,1 and 2,3)
+            float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
             {
                 const int o = (yl + 2) * T::PW + 4 * tx;      // tile entry of (x = xq - 2, y)
                 // plane z: rows y-1, y, y+1 over x-2 .. x+5; rows y-2, y+2 over x .. x+3
@@ -859,14 +502,6 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
                 *reinterpret_cast<float2*>(k2 + 2) = *reinterpret_cast<const float2*>(Pm2 + o + 4);
                 *reinterpret_cast<float2*>(l2) = *reinterpret_cast<const float2*>(Pp2 + o + 2);
                 *reinterpret_cast<float2*>(l2 + 2) = *reinterpret_cast<const float2*>(Pp2 + o + 4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float f0 = b[j + 2];
-                    H[j].xx = __fmul_rn(__fsub_rn(__fsub_rn(b[j + 4], f0), __fsub_rn(f0, b[j])), qs);
-                    H[j].yy = __fmul_rn(__fsub_rn(__fsub_rn(u2[j], f0), __fsub_rn(f0, t2[j])), qs);
-                    H[j].zz = __fmul_rn(__fsub_rn(__fsub_rn(l2[j], f0), __fsub_rn(f0, k2[j])), qs);
-                    H[j].xy = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 3], c[j + 1]), __fsub_rn(a[j + 3], a[j + 1])), qs);
-                }
                 // planes z-1, z+1: row y over x-1 .. x+4 (loaded as x-2 .. x+5), rows y-1, y+1 over x .. x+3
                 float mm[8], nn[8], mu[4], md[4], nu[4], nd[4];
                 *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(Pm1 + o);
@@ -881,61 +516,77 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
                 *reinterpret_cast<float2*>(nu + 2) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 4);
                 *reinterpret_cast<float2*>(nd) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 2);
                 *reinterpret_cast<float2*>(nd + 2) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 4);
+                const float2 qs2 = make_float2(qs, qs);
+                // (hi - mid) - (mid - lo), then * sigma^2/4: FADD2 / FMUL2 round each lane exactly like
+                // the scalar __fsub_rn / __fmul_rn chain (no multiply feeds an add, so nothing can fuse)
+#define PAIR(arr, i) make_float2((arr)[(i)], (arr)[(i) + 1])
+#define DD(hi, mid, lo) vmul(vsub(vsub(hi, mid), vsub(mid, lo)), qs2)
+#define DX(hi1, lo1, hi0, lo0) vmul(vsub(vsub(hi1, lo1), vsub(hi0, lo0)), qs2)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    H[j].xz = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 3], nn[j + 1]), __fsub_rn(mm[j + 3], mm[j + 1])), qs);
-                    H[j].yz = __fmul_rn(__fsub_rn(__fsub_rn(nd[j], nu[j]), __fsub_rn(md[j], mu[j])), qs);
+                for (int g = 0; g < 2; ++g) {
+                    const int j = 2 * g;
+                    const float2 f0 = PAIR(b, j + 2);
+                    Hxx[g] = DD(PAIR(b, j + 4), f0, PAIR(b, j));
+                    Hyy[g] = DD(PAIR(u2, j), f0, PAIR(t2, j));
+                    Hzz[g] = DD(PAIR(l2, j), f0, PAIR(k2, j));
+                    Hxy[g] = DX(PAIR(c, j + 3), PAIR(c, j + 1), PAIR(a, j + 3), PAIR(a, j + 1));
+                    Hxz[g] = DX(PAIR(nn, j + 3), PAIR(nn, j + 1), PAIR(mm, j + 3), PAIR(mm, j + 1));
+                    Hyz[g] = DX(PAIR(nd, j), PAIR(nu, j), PAIR(md, j), PAIR(mu, j));
                 }
+#undef PAIR
+#undef DD
+#undef DX
             }
 
             const long long i0 = ((long long)(z - p.z_begin) * h + y) * w + xq;
-            if (MODE == 2) {
+            if (MODE == 2 || !all_x) {            // stage dump; quads that straddle an x face; unaligned widths
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (m[j]) {
-                        p.D[0][i0 + j] = H[j].zz; p.D[1][i0 + j] = H[j].yy; p.D[2][i0 + j] = H[j].yz;
-                        p.D[3][i0 + j] = H[j].xx; p.D[4][i0 + j] = H[j].xy; p.D[5][i0 + j] = H[j].xz;
-                    }
-                continue;
-            }
-            if (!all_x) {                         // quads that straddle an x face, or an unaligned width
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (m[j]) {
-                        const float jv = voxel_update<MODE>(p, i0 + j, H[j]);
-                        vmin = fminf(vmin, jv); vmax = fmaxf(vmax, jv);
+                        typedef Lanes<float2> L2;
+                        Hess H;
+                        H.xx = L2::get(Hxx[j >> 1], j & 1); H.xy = L2::get(Hxy[j >> 1], j & 1);
+                        H.xz = L2::get(Hxz[j >> 1], j & 1); H.yy = L2::get(Hyy[j >> 1], j & 1);
+                        H.yz = L2::get(Hyz[j >> 1], j & 1); H.zz = L2::get(Hzz[j >> 1], j & 1);
+                        if (MODE == 2) {
+                            p.D[0][i0 + j] = H.zz; p.D[1][i0 + j] = H.yy; p.D[2][i0 + j] = H.yz;
+                            p.D[3][i0 + j] = H.xx; p.D[4][i0 + j] = H.xy; p.D[5][i0 + j] = H.xz;
+                        } else {
+                            const float jv = voxel_update<MODE == 2 ? 0 : MODE>(p, i0 + j, H);
+                            vmin = fminf(vmin, jv); vmax = fmaxf(vmax, jv);
+                        }
                     }
                 continue;
             }
             float jold[4] = { 0.f, 0.f, 0.f, 0.f };
             if (MODE == 1) *reinterpret_cast<float4*>(jold) = *reinterpret_cast<const float4*>(p.J + i0);
             float jn[4];
-            uint8_t cx[4], cy[4], cz[4];
+            uint32_t cx = 0, cy = 0, cz = 0;      // four direction codes each, byte j = voxel j
             float ex[4], ey[4], ez[4];
             bool wr[4];
 #pragma unroll
-            for (int j = 0; j < 4; j += 2) {
+            for (int g = 0; g < 2; ++g) {
+                const int j = 2 * g;
                 Eig3x2 e;
-                eig_sym3_x2(make_float2(H[j].xx, H[j + 1].xx), make_float2(H[j].xy, H[j + 1].xy),
-                            make_float2(H[j].xz, H[j + 1].xz), make_float2(H[j].yy, H[j + 1].yy),
-                            make_float2(H[j].yz, H[j + 1].yz), make_float2(H[j].zz, H[j + 1].zz), e);
-                const P2 v = vesselness_x2(e, p.k);
+                eig_sym3<float2>(Hxx[g], Hxy[g], Hxz[g], Hyy[g], Hyz[g], Hzz[g], e);
+                const float2 v = vesselness<float2>(e, p.k);
                 wr[j] = MODE == 0 || v.x > jold[j];
                 wr[j + 1] = MODE == 0 || v.y > jold[j + 1];
                 jn[j] = wr[j] ? v.x : jold[j];
                 jn[j + 1] = wr[j + 1] ? v.y : jold[j + 1];
-                cx[j] = dir_code(e.vx.x); cy[j] = dir_code(e.vy.x); cz[j] = dir_code(e.vz.x);
-                cx[j + 1] = dir_code(e.vx.y); cy[j + 1] = dir_code(e.vy.y); cz[j + 1] = dir_code(e.vz.y);
+                cx |= (dir_code(e.vx.x) << (8 * j)) | (dir_code(e.vx.y) << (8 * j + 8));
+                cy |= (dir_code(e.vy.x) << (8 * j)) | (dir_code(e.vy.y) << (8 * j + 8));
+                cz |= (dir_code(e.vz.x) << (8 * j)) | (dir_code(e.vz.y) << (8 * j + 8));
                 ex[j] = e.vx.x; ey[j] = e.vy.x; ez[j] = e.vz.x;
                 ex[j + 1] = e.vx.y; ey[j + 1] = e.vy.y; ez[j + 1] = e.vz.y;
                 vmin = fminf(vmin, fminf(jn[j], jn[j + 1])); vmax = fmaxf(vmax, fmaxf(jn[j], jn[j + 1]));
             }
             if (MODE == 0) {
                 *reinterpret_cast<float4*>(p.J + i0) = make_float4(jn[0], jn[1], jn[2], jn[3]);
-                *reinterpret_cast<uchar4*>(p.Vx + i0) = make_uchar4(cx[0], cx[1], cx[2], cx[3]);
-                *reinterpret_cast<uchar4*>(p.Vy + i0) = make_uchar4(cy[0], cy[1], cy[2], cy[3]);
-                *reinterpret_cast<uchar4*>(p.Vz + i0) = make_uchar4(cz[0], cz[1], cz[2], cz[3]);
-                if (p.scale_idx) *reinterpret_cast<uchar4*>(p.scale_idx + i0) = make_uchar4(0, 0, 0, 0);
+                *reinterpret_cast<uint32_t*>(p.Vx + i0) = cx;
+                *reinterpret_cast<uint32_t*>(p.Vy + i0) = cy;
+                *reinterpret_cast<uint32_t*>(p.Vz + i0) = cz;
+                if (p.scale_idx) *reinterpret_cast<uint32_t*>(p.scale_idx + i0) = 0u;
                 if (p.dir) {
                     *reinterpret_cast<float4*>(p.dir + i0) = make_float4(ex[0], ex[1], ex[2], ex[3]);
                     *reinterpret_cast<float4*>(p.dir + p.voxels + i0) = make_float4(ey[0], ey[1], ey[2], ey[3]);
@@ -946,7 +597,9 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (wr[j]) {
-                        p.Vx[i0 + j] = cx[j]; p.Vy[i0 + j] = cy[j]; p.Vz[i0 + j] = cz[j];
+                        p.Vx[i0 + j] = (uint8_t)(cx >> (8 * j));
+                        p.Vy[i0 + j] = (uint8_t)(cy >> (8 * j));
+                        p.Vz[i0 + j] = (uint8_t)(cz >> (8 * j));
                         if (p.scale_idx) p.scale_idx[i0 + j] = (uint8_t)p.scale;
                         if (p.dir) {
                             p.dir[i0 + j] = ex[j];
@@ -1038,16 +691,16 @@ vesselness_stage_kernel(const float* __restrict__ Dxx, const float* __restrict__
     float v[2], ev[2][3], el[2][3];
     if (i + 1 < n) {
         Eig3x2 e;
-        eig_sym3_x2(make_float2(Dxx[i], Dxx[i + 1]), make_float2(Dxy[i], Dxy[i + 1]), make_float2(Dxz[i], Dxz[i + 1]),
-                    make_float2(Dyy[i], Dyy[i + 1]), make_float2(Dyz[i], Dyz[i + 1]), make_float2(Dzz[i], Dzz[i + 1]), e);
-        const P2 vv = vesselness_x2(e, k);
+        eig_sym3<float2>(make_float2(Dxx[i], Dxx[i + 1]), make_float2(Dxy[i], Dxy[i + 1]), make_float2(Dxz[i], Dxz[i + 1]),
+                         make_float2(Dyy[i], Dyy[i + 1]), make_float2(Dyz[i], Dyz[i + 1]), make_float2(Dzz[i], Dzz[i + 1]), e);
+        const float2 vv = vesselness<float2>(e, k);
         v[0] = vv.x; v[1] = vv.y;
         ev[0][0] = e.vx.x; ev[0][1] = e.vy.x; ev[0][2] = e.vz.x; ev[1][0] = e.vx.y; ev[1][1] = e.vy.y; ev[1][2] = e.vz.y;
         el[0][0] = e.l1.x; el[0][1] = e.l2.x; el[0][2] = e.l3.x; el[1][0] = e.l1.y; el[1][1] = e.l2.y; el[1][2] = e.l3.y;
     } else {
         Eig3 e;
-        eig_sym3(Dxx[i], Dxy[i], Dxz[i], Dyy[i], Dyz[i], Dzz[i], e);
-        v[0] = vesselness(e, k);
+        eig_sym3<float>(Dxx[i], Dxy[i], Dxz[i], Dyy[i], Dyz[i], Dzz[i], e);
+        v[0] = vesselness<float>(e, k);
         ev[0][0] = e.vx; ev[0][1] = e.vy; ev[0][2] = e.vz; el[0][0] = e.l1; el[0][1] = e.l2; el[0][2] = e.l3;
     }
     for (int q = 0; q < 2 && i + q < n; ++q) {
@@ -1068,8 +721,8 @@ vesselness_stage_scalar_kernel(const float* __restrict__ Dxx, const float* __res
     const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
     Eig3 e;
-    eig_sym3(Dxx[i], Dxy[i], Dxz[i], Dyy[i], Dyz[i], Dzz[i], e);
-    v_out[i] = vesselness(e, k);
+    eig_sym3<float>(Dxx[i], Dxy[i], Dxz[i], Dyy[i], Dyz[i], Dzz[i], e);
+    v_out[i] = vesselness<float>(e, k);
     if (dir_out) { dir_out[i] = e.vx; dir_out[n + i] = e.vy; dir_out[2 * n + i] = e.vz; }
     if (lambda_out) { lambda_out[3 * i] = e.l1; lambda_out[3 * i + 1] = e.l2; lambda_out[3 * i + 2] = e.l3; }
 }
