@@ -313,9 +313,8 @@ __device__ __noinline__ Hess hessian_at_face(const Field& f, int x, int y, int z
 // central difference touches live in a six-slot shared-memory ring of
 // (16+4) x (128+4) tiles (slot = plane mod 6, so the plane being staged never
 // aliases one being read and one __syncthreads per plane suffices).  The next
-// plane's tile is fetched from global memory into registers before the current
-// plane is processed and parked in the ring afterwards, so the loads are in
-// flight during the per-voxel stage.  A thread produces 4 consecutive x voxels
+// plane's tile is copied global -> shared with cp.async (LDGSTS, 8-byte units,
+// no staging registers) while the current plane is processed.  A thread produces 4 consecutive x voxels
 // of 2 rows per plane: window rows are read with 128-bit / 64-bit shared loads
 // (6.5 loads per voxel) and results leave as float4 / uchar4 stores.  Voxels at
 // least two steps from every volume face take the closed interior form,
@@ -352,15 +351,17 @@ struct FView {
 };
 
 #ifndef HESS_MIN_CTAS
-#define HESS_MIN_CTAS 2
+#define HESS_MIN_CTAS 3
+#endif
+#ifndef HESS_RPT
+#define HESS_RPT 2      // tile rows per thread (2: 256-thread CTAs, 1: 512-thread CTAs)
 #endif
 struct HessTile {
-    static constexpr int TX = 128, TY = 16, NT = 256;
+    static constexpr int TX = 128, TY = 16, RPT = HESS_RPT, NT = 32 * TY / RPT;
     static constexpr int PW = TX + 4;            // 132 floats per tile row (16-byte multiple)
     static constexpr int PH = TY + 4;
     static constexpr int PLANE = PW * PH;        // 2640 floats
     static constexpr int SLOTS = 6;
-    static constexpr int LOADS = (PLANE + NT - 1) / NT;   // 11 staged values per thread
     static constexpr int SMEM_BYTES = SLOTS * PLANE * 4;  // 63360
 };
 
@@ -427,33 +428,38 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
     const int ze = min(min(p.z_begin + (bz + 1) * p.zchunk, p.z_begin + p.nz), l - 2);
     if (zs >= ze) return;
 
-    // staging map: this thread's k-th tile entry and its (clamped) global offset, plane-independent
-    int g_off[T::LOADS];
+    // staging map: the tile as 8-byte units (x0 is even, so every unit is 8-byte aligned in global memory);
+    // this thread's k-th unit, its shared-memory byte offset and global element offset, plane-independent.
+    // Units outside the volume are zero-filled: interior voxels never read them.
+    constexpr int UNITS = T::PLANE / 2, UPR = T::PW / 2;
+    constexpr int NU = (UNITS + T::NT - 1) / T::NT;           // 6 units per thread
+    int g_off[NU];
+    unsigned ok_mask = 0;
 #pragma unroll
-    for (int k = 0; k < T::LOADS; ++k) {
+    for (int k = 0; k < NU; ++k) {
         const int e = tid + k * T::NT;
-        const int r = e / T::PW, c = e - r * T::PW;
-        g_off[k] = clampi(y0 + r, 0, h - 1) * p.f.fpitch + clampi(x0 + c, 0, w - 1);
+        const int r = e / UPR, c = 2 * (e - r * UPR);
+        const int gy = y0 + r, gx = x0 + c;
+        const bool ok = e < UNITS && gy >= 0 && gy < h && gx >= 0 && gx < w;
+        g_off[k] = ok ? gy * p.f.fpitch + gx : 0;
+        ok_mask |= (ok ? 1u : 0u) << k;
     }
-    constexpr int LAST_FULL = T::PLANE / T::NT;               // entries k < LAST_FULL exist for every thread
-    const bool tail = tid + LAST_FULL * T::NT < T::PLANE;
-    float stage[T::LOADS];
-    auto fetch = [&](int plane) {
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    auto fetch = [&](int plane) {             // asynchronous global -> shared copy of one plane's tile
         const float* __restrict__ src = p.f.F + (long long)(plane - p.f.base) * p.f.fplane;
+        const unsigned dst = ring_s + ((plane % T::SLOTS) * T::PLANE + 2 * tid) * 4;
 #pragma unroll
-        for (int k = 0; k < T::LOADS; ++k)
-            if (k < LAST_FULL || tail) stage[k] = __ldg(src + g_off[k]);
-    };
-    auto park = [&](int plane) {
-        float* dst = ring + (plane % T::SLOTS) * T::PLANE + tid;
-#pragma unroll
-        for (int k = 0; k < T::LOADS; ++k)
-            if (k < LAST_FULL || tail) dst[k * T::NT] = stage[k];
+        for (int k = 0; k < NU; ++k)
+            if (tid + k * T::NT < UNITS) {
+                const int nbytes = (ok_mask >> k) & 1u ? 8 : 0;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + k * T::NT * 8),
+                             "l"(src + g_off[k]), "r"(nbytes) : "memory");
+            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    // prologue: planes zs-2 .. zs+1 into the ring, zs+2 in flight (all inside the volume)
-    for (int q = zs - 2; q <= zs + 1; ++q) { fetch(q); park(q); }
-    fetch(zs + 2);
+    // prologue: planes zs-2 .. zs+2 on their way into the ring (all inside the volume)
+    for (int q = zs - 2; q <= zs + 2; ++q) fetch(q);
 
     const int xq = bx * T::TX + 4 * tx;          // first of this thread's 4 x voxels
     bool m[4];                                   // voxel is interior in x
@@ -465,9 +471,9 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
     float vmin = 3.4e38f, vmax = 0.0f;
 
     for (int z = zs; z < ze; ++z) {
-        park(z + 2);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                          // plane z+2 visible; everyone is done with plane z-3's slot
-        if (z + 1 < ze) fetch(z + 3);
+        if (z + 1 < ze) fetch(z + 3);             // lands in that slot while plane z is processed
 
         const float* P0 = ring + (z % T::SLOTS) * T::PLANE;
         const float* Pm1 = ring + ((z - 1) % T::SLOTS) * T::PLANE;
@@ -476,8 +482,8 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
         const float* Pp2 = ring + ((z + 2) % T::SLOTS) * T::PLANE;
 
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int yl = ty + 8 * half;         // row inside the tile
+        for (int half = 0; half < T::RPT; ++half) {
+            const int yl = ty + (T::TY / T::RPT) * half;   // row inside the tile
             const int y = by * T::TY + yl;
             if (y < 2 || y > h - 3 || !any_x) continue;
             // second differences of the quad as two packed pairs (voxels 0,1 and 2,3)
