@@ -323,6 +323,27 @@ int launch_xy(frangi_gpu* H, Slab& s, const ScalePlan& sp, const uint8_t* I_own,
     return launch_xy_e<true>(sp.rxy_t, p, sp.txy, (int)nblocks, s.s_main);
 }
 
+template <int L, bool EXACT>
+int launch_zm_t(const ZParams& p, const GaussTaps& t, long long nblocks, cudaStream_t s)
+{
+    gauss_z_march_kernel<L, EXACT><<<(unsigned)nblocks, 128, 0, s>>>(p, t);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <bool EXACT>
+int launch_zm_e(int L, const ZParams& p, const GaussTaps& t, long long nblocks, cudaStream_t s)
+{
+    switch (L) {
+        case 3: return launch_zm_t<3, EXACT>(p, t, nblocks, s);
+        case 6: return launch_zm_t<6, EXACT>(p, t, nblocks, s);
+        case 9: return launch_zm_t<9, EXACT>(p, t, nblocks, s);
+        case 12: return launch_zm_t<12, EXACT>(p, t, nblocks, s);
+    }
+    return fail(FRANGI_GPU_EINVAL, "no marching gauss_z instantiation for radius %d", L);
+}
+
 int launch_z(frangi_gpu* H, Slab& s, const ScalePlan& sp)
 {
     ZParams p;
@@ -331,11 +352,26 @@ int launch_z(frangi_gpu* H, Slab& s, const ScalePlan& sp)
     p.fpitch = H->fpitch; p.fplane = H->fplane;
     p.in_base = s.xb; p.in_count = s.xe - s.xb;
     p.out_base = s.fb; p.out_count = s.fe - s.fb;
+    const bool fma = (H->flags & FRANGI_GPU_FLAG_FMA_SMOOTHING) != 0;
+    if (sp.rz_t <= 12) {
+        // marching form: one chunk per column unless the plane alone cannot fill the GPU
+        p.nxs = (H->w + 255) / 256;
+        const long long cols = (long long)p.nxs * H->h;
+        long long nzc = std::max<long long>(1, std::min<long long>((1184 + cols - 1) / cols, (p.out_count + 15) / 16));
+        p.zchunk = (int)((p.out_count + nzc - 1) / nzc);
+        nzc = (p.out_count + p.zchunk - 1) / p.zchunk;
+        p.nzc = (int)nzc;
+        const long long nblocks = cols * nzc;
+        if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+        if (fma) return launch_zm_e<false>(sp.rz_t, p, sp.tz, nblocks, s.s_main);
+        return launch_zm_e<true>(sp.rz_t, p, sp.tz, nblocks, s.s_main);
+    }
+    p.zchunk = 8;
     p.nzc = (p.out_count + 7) / 8;
     p.nxs = (H->w + 127) / 128;
     const long long nblocks = (long long)p.nzc * p.nxs * H->h;
     if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
-    if (H->flags & FRANGI_GPU_FLAG_FMA_SMOOTHING) return launch_z_e<false>(sp.rz_t, p, sp.tz, nblocks, s.s_main);
+    if (fma) return launch_z_e<false>(sp.rz_t, p, sp.tz, nblocks, s.s_main);
     return launch_z_e<true>(sp.rz_t, p, sp.tz, nblocks, s.s_main);
 }
 

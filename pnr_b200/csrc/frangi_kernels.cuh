@@ -217,6 +217,7 @@ struct ZParams {
     int out_base;
     int out_count;      // planes to produce
     int nzc, nxs;       // z chunks, x strips
+    int zchunk;         // output planes per chunk (marching form)
 };
 
 template <int LZ, bool EXACT>
@@ -253,6 +254,66 @@ gauss_z_kernel(const __grid_constant__ ZParams p, const __grid_constant__ GaussT
     for (int o = 0; o < RZ; ++o) {
         const int zo = zc * RZ + o;
         if (zo < p.out_count) dst[(long long)zo * p.fplane] = acc[o];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2 (marching form, radius <= 12): z Gaussian pass as a register sliding
+// window.  A thread owns two adjacent x columns and marches along z through
+// its chunk; the 2LZ+1 inputs of the current output (plus PF planes of
+// prefetch, so that several loads per thread are in flight) live in a register
+// ring whose indices are static because the march is unrolled by the ring
+// period.  Every input plane is read once per chunk and every output needs one
+// 8-byte load, one 8-byte store and 2LZ+1 multiply-adds: the pass runs at the
+// HBM rate.  Accumulation order is the reference's (ascending taps from zero,
+// frangi.cpp:756-768), replicate clamping against the GLOBAL volume ends only.
+// ---------------------------------------------------------------------------
+template <int LZ, bool EXACT>
+__global__ void __launch_bounds__(128)
+gauss_z_march_kernel(const __grid_constant__ ZParams p, const __grid_constant__ GaussTaps taps)
+{
+    constexpr int PF = 3;
+    constexpr int Q = 2 * LZ + 1 + PF;            // ring period
+    const long long bid = blockIdx.x;
+    const int xs = (int)(bid % p.nxs);
+    const long long rest = bid / p.nxs;
+    const int y = (int)(rest % p.h);
+    const int zc = (int)(rest / p.h);
+    const int x = xs * 256 + 2 * threadIdx.x;
+    if (x >= p.w) return;
+    const int t_begin = zc * p.zchunk;             // first output plane (relative to out_base) of this chunk
+    const int nout = min(p.zchunk, p.out_count - t_begin);
+    const int zg0 = p.out_base + t_begin;          // global plane of the first output
+    const float2* __restrict__ col = reinterpret_cast<const float2*>(p.in + (long long)y * p.fpitch + x);
+    float2* __restrict__ dst = reinterpret_cast<float2*>(p.out + ((long long)t_begin * p.fplane + (long long)y * p.fpitch + x));
+    const long long plane2 = p.fplane / 2;         // float2 units per plane (fpitch is even)
+    auto ld = [&](int j) {                         // input j of the chunk = global plane zg0 - LZ + j, clamped
+        const int zs = clampi(clampi(zg0 - LZ + j, 0, p.l - 1) - p.in_base, 0, p.in_count - 1);
+        return __ldcs(col + (long long)zs * plane2);
+    };
+    float2 win[Q];
+#pragma unroll
+    for (int j = 0; j < Q - 1; ++j) win[j] = ld(j);
+    for (int t0 = 0; t0 < nout; t0 += Q) {
+#pragma unroll
+        for (int s = 0; s < Q; ++s) {
+            const int t = t0 + s;
+            if (t < nout) {
+                win[(s + Q - 1) % Q] = ld(t + Q - 1);
+                float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int k = 0; k <= 2 * LZ; ++k) {
+                    const float2 v = win[(s + k) % Q];
+                    if (EXACT) {
+                        acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, taps.g[k]));
+                        acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, taps.g[k]));
+                    } else {
+                        acc = __ffma2_rn(v, make_float2(taps.g[k], taps.g[k]), acc);
+                    }
+                }
+                __stcs(dst + (long long)t * plane2, acc);
+            }
+        }
     }
 }
 
