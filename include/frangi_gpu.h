@@ -48,7 +48,11 @@ enum {
     /* keep an unquantised float32 direction (3 planar volumes x,y,z) */
     FRANGI_GPU_FLAG_DIR_F32 = 2,
     /* keep the arg-max scale index per voxel (uint8) */
-    FRANGI_GPU_FLAG_SCALE_IDX = 4
+    FRANGI_GPU_FLAG_SCALE_IDX = 4,
+    /* frangi_gpu_create with ndev > 1: move halos with peer copies inside the process
+     * instead of NCCL send/recv (implied when device_ids repeats a device, which is how
+     * the slab decomposition is exercised on a single GPU) */
+    FRANGI_GPU_FLAG_LOCAL_HALO = 8
 };
 
 /* ---- whole-volume handle, one process driving ndev devices ---------------

@@ -1,0 +1,74 @@
+// frangi.h -- source-compatible stand-in for the hot-path part of the reference's
+// `class Frangi` (pnr-vaa3d/frangi.h:5-59), so that the reference's only call
+// site compiles unchanged against the GPU library:
+//
+//     Frangi frangiflt(sigs, zdist, alpha, beta, C, beta_one, beta_two);    // Advantra_plugin.cpp:2488
+//     frangiflt.frangi3d(data1d, N, M, P, J, Jmin, Jmax, Vx, Vy, Vz);       // Advantra_plugin.cpp:2496
+//
+// Same public field names, constructor and member signatures as the reference for
+// everything ON the path (frangi.h:8-24,33,35,42); every call forwards to the C-ABI
+// of include/frangi_gpu.h.  Members that are off the path (frangi2d, the soma
+// helpers imerode/imdilate/xy-imgaussian, the direction tables, the public
+// eigen-solver entry points) are not provided here: an integrator who needs them
+// keeps the reference's frangi.cpp under another class name.
+//
+// Error behaviour: the reference's members return void and fail only by uncaught
+// std::bad_alloc; here a failed GPU call throws std::runtime_error carrying
+// frangi_gpu_last_error().  There is no CPU fallback.
+#ifndef PNR_B200_FRANGI_SHIM_H
+#define PNR_B200_FRANGI_SHIM_H
+
+#include <vector>
+
+struct frangi_gpu;   // opaque handle of include/frangi_gpu.h
+
+class Frangi {
+public:
+    // ---- the reference's public fields (frangi.h:8-22) ----
+    std::vector<float> sig;
+    float zdist;
+    float alpha;
+    float beta;
+    float BetaOne;   // 2-D only; kept so that the constructor signature matches
+    float BetaTwo;   // 2-D only
+    float C;
+    bool blackwhite; // true: dark ridges, false: bright ridges (default, frangi.cpp:54)
+
+    // ---- additions (defaults keep the reference's behaviour) ----
+    std::vector<int> devices;   // CUDA devices to shard z-slabs over; empty = device 0
+    unsigned flags;             // FRANGI_GPU_FLAG_* of include/frangi_gpu.h; 0 = bit-exact smoothing
+
+    Frangi(std::vector<float> sigs, float zdist_, float alpha_, float beta_, float C_, float beta_one, float beta_two);
+    ~Frangi();
+    Frangi(const Frangi&) = delete;
+    Frangi& operator=(const Frangi&) = delete;
+
+    // frangi.h:33 -- caller owns every buffer (w*h*l elements each), callee only fills
+    void frangi3d(unsigned char* I, int w, int h, int l, float* J, float& Jmin, float& Jmax,
+                  unsigned char* Vx, unsigned char* Vy, unsigned char* Vz);
+
+    // As above plus the 8-bit normalisation the caller applies next (Advantra_plugin.cpp:2499-2512)
+    // done on the device; J may be NULL (the caller frees it at once, :2514).
+    void frangi3d_j8(unsigned char* I, int w, int h, int l, float* J, float& Jmin, float& Jmax,
+                     unsigned char* Vx, unsigned char* Vy, unsigned char* Vz, unsigned char* J8);
+
+    // frangi.h:35
+    void hessian3d(unsigned char* I, int w, int h, int l, float sig_, float zdist_,
+                   float* Dzz, float* Dyy, float* Dyz, float* Dxx, float* Dxy, float* Dxz);
+
+    // frangi.h:42
+    static void imgaussian(unsigned char* I, int w, int h, int l, float sig_, float zdist_, float* F);
+
+private:
+    frangi_gpu* handle_;
+    int hw_, hh_, hl_;
+    std::vector<float> hsig_;
+    float hz_, ha_, hb_, hc_;
+    bool hbw_;
+    unsigned hflags_;
+    std::vector<int> hdev_;
+    void ensure_handle(int w, int h, int l);
+    void release();
+};
+
+#endif

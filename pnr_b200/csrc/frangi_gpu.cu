@@ -179,7 +179,8 @@ struct Slab {
     int* dMinMax = nullptr;
     int* hMinMax = nullptr;   // pinned
     cudaStream_t s_main = nullptr, s_comm = nullptr;
-    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
+    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr, ev_done = nullptr;
+    int* dGather = nullptr;   // local-copy mode, slab 0 only: min/max of every slab
     std::vector<cudaEvent_t> ev_all;    // timing_depth sets of (4 per scale + 2) events
     cudaEvent_t* ev_time = nullptr;     // the set of the run being recorded
     ncclx::ncclComm_t comm = nullptr;
@@ -199,6 +200,7 @@ struct frangi_gpu {
     std::vector<ScalePlan> scales;
     std::vector<Slab> slabs;     // slabs driven by this process
     bool ran = false;
+    bool local_halo = false;     // halos move by peer copies inside this process instead of NCCL
     int timing_depth = 1;        // event sets kept per slab
     long long runs_recorded = 0; // runs since the last frangi_gpu_timing_depth call
     float last_ms[8] = { 0 };
@@ -217,6 +219,8 @@ void free_slab(Slab& s)
     for (auto e : s.ev_all) cudaEventDestroy(e);
     if (s.ev_boundary) cudaEventDestroy(s.ev_boundary);
     if (s.ev_halo) cudaEventDestroy(s.ev_halo);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    cudaFree(s.dGather);
     if (s.s_main) cudaStreamDestroy(s.s_main);
     if (s.s_comm) cudaStreamDestroy(s.s_comm);
     s = Slab();
@@ -279,6 +283,7 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     CK(cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&s.ev_boundary, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_halo, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     s.ev_all.resize(4 * H->scales.size() + 2);
     for (auto& e : s.ev_all) CK(cudaEventCreate(&e));
     s.ev_time = s.ev_all.data();
@@ -471,9 +476,42 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
 // neighbours.  Slab k sends its lowest `halo` own planes down and its highest
 // `halo` own planes up, and receives the matching planes into the halo regions
 // of its Fxy buffer.  All calls of all local slabs sit in one NCCL group.
+// Local-copy form (every slab lives in this process; used when device ids repeat or
+// FRANGI_GPU_FLAG_LOCAL_HALO is set): each slab PULLS its halo planes from its neighbours'
+// boundary planes with peer copies on its comm stream, after both its own and the
+// neighbour's boundary smoothing.  The neighbour may not overwrite those planes for the next
+// scale before the pull is done: run_pipeline makes each slab wait for its neighbours'
+// ev_halo of the previous scale before it smooths again.
+int exchange_halos_local(frangi_gpu* H, int halo)
+{
+    const size_t plane = (size_t)H->fplane;
+    for (size_t k = 0; k < H->slabs.size(); ++k) {
+        Slab& s = H->slabs[k];
+        CK(cudaSetDevice(s.dev));
+        if (k > 0) {
+            Slab& nb = H->slabs[k - 1];
+            const int n_recv = s.zb - std::max(s.zb - halo, 0);
+            CK(cudaStreamWaitEvent(s.s_comm, nb.ev_boundary, 0));
+            CK(cudaMemcpyPeerAsync(s.dFxy + (size_t)(s.zb - n_recv - s.xb) * plane, s.dev,
+                                   nb.dFxy + (size_t)(nb.ze - n_recv - nb.xb) * plane, nb.dev,
+                                   (size_t)n_recv * plane * sizeof(float), s.s_comm));
+        }
+        if (k + 1 < H->slabs.size()) {
+            Slab& nb = H->slabs[k + 1];
+            const int n_recv = std::min(s.ze + halo, H->l) - s.ze;
+            CK(cudaStreamWaitEvent(s.s_comm, nb.ev_boundary, 0));
+            CK(cudaMemcpyPeerAsync(s.dFxy + (size_t)(s.ze - s.xb) * plane, s.dev,
+                                   nb.dFxy + (size_t)(nb.zb - nb.xb) * plane, nb.dev,
+                                   (size_t)n_recv * plane * sizeof(float), s.s_comm));
+        }
+    }
+    return 0;
+}
+
 int exchange_halos(frangi_gpu* H, int halo)
 {
     if (H->nslabs_total == 1) return 0;
+    if (H->local_halo) return exchange_halos_local(H, halo);
     auto& N = ncclx::api();
     const size_t plane = (size_t)H->fplane;
     NK(N.GroupStart());
@@ -523,6 +561,10 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
             for (size_t k = 0; k < H->slabs.size(); ++k) {
                 Slab& s = H->slabs[k];
                 CK(cudaSetDevice(s.dev));
+                if (H->local_halo && si > 0) {   // neighbours have pulled the previous scale's boundary planes
+                    if (k > 0) CK(cudaStreamWaitEvent(s.s_main, H->slabs[k - 1].ev_halo, 0));
+                    if (k + 1 < H->slabs.size()) CK(cudaStreamWaitEvent(s.s_main, H->slabs[k + 1].ev_halo, 0));
+                }
                 const int nz = s.ze - s.zb;
                 if (nz <= 2 * halo) {
                     RC(launch_xy(H, s, sp, I_own[k], s.zb, s.ze));
@@ -561,7 +603,32 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
         }
     }
     // global Jmin / Jmax across slabs, then the 8-bit normalisation
-    if (multi) {
+    if (multi && H->local_halo) {
+        // gather every slab's pair on slab 0, reduce there, hand the result back
+        Slab& s0 = H->slabs[0];
+        const int n = (int)H->slabs.size();
+        for (int k = 0; k < n; ++k) {
+            Slab& s = H->slabs[k];
+            CK(cudaSetDevice(s.dev));
+            CK(cudaEventRecord(s.ev_done, s.s_main));
+        }
+        CK(cudaSetDevice(s0.dev));
+        for (int k = 0; k < n; ++k) {
+            Slab& s = H->slabs[k];
+            CK(cudaStreamWaitEvent(s0.s_main, s.ev_done, 0));
+            CK(cudaMemcpyPeerAsync(s0.dGather + 2 * k, s0.dev, s.dMinMax, s.dev, 2 * sizeof(int), s0.s_main));
+        }
+        minmax_reduce_kernel<<<1, 32, 0, s0.s_main>>>(s0.dGather, n, s0.dMinMax);
+        g_launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(s0.ev_done, s0.s_main));
+        for (int k = 1; k < n; ++k) {
+            Slab& s = H->slabs[k];
+            CK(cudaSetDevice(s.dev));
+            CK(cudaStreamWaitEvent(s.s_main, s0.ev_done, 0));
+            CK(cudaMemcpyPeerAsync(s.dMinMax, s.dev, s0.dMinMax, s0.dev, 2 * sizeof(int), s.s_main));
+        }
+    } else if (multi) {
         auto& N = ncclx::api();
         NK(N.GroupStart());
         for (auto& s : H->slabs) {
@@ -727,7 +794,25 @@ FRANGI_API int frangi_gpu_create(frangi_gpu_t** out, const float* sigmas, int ns
             rc = alloc_slab(H, H->slabs[k], devs[k], k, zb, ze);
         }
     }
-    if (!rc && nuse > 1) {
+    bool repeated = false;
+    for (int a = 0; a < nuse; ++a)
+        for (int b = a + 1; b < nuse; ++b) repeated |= devs[a] == devs[b];
+    H->local_halo = nuse > 1 && (repeated || (flags & FRANGI_GPU_FLAG_LOCAL_HALO));
+    if (!rc && H->local_halo) {
+        cudaError_t e = cudaSetDevice(devs[0]);
+        if (e == cudaSuccess) e = cudaMalloc(&H->slabs[0].dGather, 2 * sizeof(int) * nuse);
+        for (int a = 0; a < nuse && e == cudaSuccess; ++a)       // peer access where the devices differ
+            for (int b = 0; b < nuse && e == cudaSuccess; ++b)
+                if (devs[a] != devs[b]) {
+                    e = cudaSetDevice(devs[a]);
+                    if (e == cudaSuccess) {
+                        const cudaError_t pe = cudaDeviceEnablePeerAccess(devs[b], 0);
+                        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                        else if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    }
+                }
+        if (e != cudaSuccess) rc = fail(FRANGI_GPU_ECUDA, "local halo setup: %s", cudaGetErrorString(e));
+    } else if (!rc && nuse > 1) {
         auto& N = ncclx::api();
         if (!N.ok) rc = fail(FRANGI_GPU_ENCCL, "libnccl.so.2 not found or incomplete");
         else {

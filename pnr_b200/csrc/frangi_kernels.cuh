@@ -834,4 +834,13 @@ j_to_j8_kernel(const float* __restrict__ J, uint8_t* __restrict__ J8, long long 
         J8[i] = j8_code(J[i], lo, range, flat);
 }
 
+// min / max over the per-slab pairs gathered on one device (local-copy multi-slab mode)
+__global__ void minmax_reduce_kernel(const int* __restrict__ pairs, int n, int* __restrict__ out)
+{
+    if (threadIdx.x != 0) return;
+    int lo = pairs[0], hi = pairs[1];
+    for (int k = 1; k < n; ++k) { lo = min(lo, pairs[2 * k]); hi = max(hi, pairs[2 * k + 1]); }
+    out[0] = lo; out[1] = hi;
+}
+
 }  // namespace frangi

@@ -1,0 +1,77 @@
+// frangi_shim.cpp -- the Frangi class of frangi.h on top of the C-ABI (include/frangi_gpu.h).
+#include "frangi.h"
+
+#include <stdexcept>
+#include <string>
+
+#include "../../include/frangi_gpu.h"
+
+namespace {
+[[noreturn]] void raise(const char* what, int rc)
+{
+    throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + frangi_gpu_last_error());
+}
+}  // namespace
+
+Frangi::Frangi(std::vector<float> sigs, float zdist_, float alpha_, float beta_, float C_, float beta_one, float beta_two)
+    : sig(sigs), zdist(zdist_), alpha(alpha_), beta(beta_), BetaOne(beta_one), BetaTwo(beta_two), C(C_),
+      blackwhite(false), flags(0), handle_(nullptr), hw_(0), hh_(0), hl_(0), hz_(0), ha_(0), hb_(0), hc_(0),
+      hbw_(false), hflags_(0)
+{
+}
+
+Frangi::~Frangi() { release(); }
+
+void Frangi::release()
+{
+    if (handle_) frangi_gpu_destroy(handle_);
+    handle_ = nullptr;
+}
+
+// The reference re-reads its public fields on every call, so the handle is rebuilt whenever
+// a field or the volume shape changed since the last call.
+void Frangi::ensure_handle(int w, int h, int l)
+{
+    const bool same = handle_ && w == hw_ && h == hh_ && l == hl_ && sig == hsig_ && zdist == hz_ && alpha == ha_ &&
+                      beta == hb_ && C == hc_ && blackwhite == hbw_ && flags == hflags_ && devices == hdev_;
+    if (same) return;
+    release();
+    const int ndev = devices.empty() ? 1 : (int)devices.size();
+    const int rc = frangi_gpu_create(&handle_, sig.data(), (int)sig.size(), zdist, alpha, beta, C, blackwhite ? 1 : 0,
+                                     w, h, l, devices.empty() ? nullptr : devices.data(), ndev, flags);
+    if (rc) { handle_ = nullptr; raise("frangi_gpu_create", rc); }
+    hw_ = w; hh_ = h; hl_ = l; hsig_ = sig; hz_ = zdist; ha_ = alpha; hb_ = beta; hc_ = C; hbw_ = blackwhite;
+    hflags_ = flags; hdev_ = devices;
+}
+
+void Frangi::frangi3d(unsigned char* I, int w, int h, int l, float* J, float& Jmin, float& Jmax,
+                      unsigned char* Vx, unsigned char* Vy, unsigned char* Vz)
+{
+    frangi3d_j8(I, w, h, l, J, Jmin, Jmax, Vx, Vy, Vz, nullptr);
+}
+
+void Frangi::frangi3d_j8(unsigned char* I, int w, int h, int l, float* J, float& Jmin, float& Jmax,
+                         unsigned char* Vx, unsigned char* Vy, unsigned char* Vz, unsigned char* J8)
+{
+    ensure_handle(w, h, l);
+    float lo = 0, hi = 0;
+    const int rc = frangi_gpu_run(handle_, I, J, &lo, &hi, Vx, Vy, Vz, J8, nullptr, nullptr);
+    if (rc) raise("frangi_gpu_run", rc);
+    Jmin = lo;
+    Jmax = hi;
+}
+
+void Frangi::hessian3d(unsigned char* I, int w, int h, int l, float sig_, float zdist_,
+                       float* Dzz, float* Dyy, float* Dyz, float* Dxx, float* Dxy, float* Dxz)
+{
+    const int dev = devices.empty() ? 0 : devices[0];
+    const int rc = frangi_gpu_hessian3d(I, w, h, l, sig_, zdist_, Dzz, Dyy, Dyz, Dxx, Dxy, Dxz, dev,
+                                        flags & FRANGI_GPU_FLAG_FMA_SMOOTHING);
+    if (rc) raise("frangi_gpu_hessian3d", rc);
+}
+
+void Frangi::imgaussian(unsigned char* I, int w, int h, int l, float sig_, float zdist_, float* F)
+{
+    const int rc = frangi_gpu_imgaussian(I, w, h, l, sig_, zdist_, F, 0, 0);
+    if (rc) raise("frangi_gpu_imgaussian", rc);
+}

@@ -29,6 +29,7 @@ LIB_PATH = os.environ.get("FRANGI_GPU_LIB") or os.path.join(_HERE, "_lib", "libf
 FLAG_FMA_SMOOTHING = 1
 FLAG_DIR_F32 = 2
 FLAG_SCALE_IDX = 4
+FLAG_LOCAL_HALO = 8
 
 _u8p = C.POINTER(C.c_uint8)
 _f32p = C.POINTER(C.c_float)
