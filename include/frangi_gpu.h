@@ -99,6 +99,13 @@ int frangi_gpu_run(frangi_gpu_t* h, const uint8_t* I_host,
                    uint8_t* Vx_host, uint8_t* Vy_host, uint8_t* Vz_host,
                    uint8_t* J8_host, uint8_t* scale_idx_host, float* dir_xyz_host);
 
+/* On a single-device handle frangi_gpu_run pipelines host->device copies, kernels and
+ * device->host copies over z chunks of `planes` planes (results are bit-identical to the
+ * one-piece run; the overlap needs pinned host buffers).  planes = 0 switches the
+ * pipelining off, -1 (default) picks max(32, 2*halo) and applies it to volumes of at least
+ * two chunks. */
+int frangi_gpu_set_stream_chunk(frangi_gpu_t* h, int planes);
+
 /* Device-resident variant (single-device handles only): I_dev is a dense uint8
  * device buffer of the handle's planes; results stay on the device and are read
  * through frangi_gpu_device_outputs.  Asynchronous on the handle's stream;

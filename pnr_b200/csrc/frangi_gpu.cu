@@ -178,7 +178,8 @@ struct Slab {
     float* dDir = nullptr;
     int* dMinMax = nullptr;
     int* hMinMax = nullptr;   // pinned
-    cudaStream_t s_main = nullptr, s_comm = nullptr;
+    cudaStream_t s_main = nullptr, s_comm = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;  // streamed run: input-ready / output-ready per chunk
     cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr, ev_done = nullptr;
     int* dGather = nullptr;   // local-copy mode, slab 0 only: min/max of every slab
     std::vector<cudaEvent_t> ev_all;    // timing_depth sets of (4 per scale + 2) events
@@ -201,6 +202,8 @@ struct frangi_gpu {
     std::vector<Slab> slabs;     // slabs driven by this process
     bool ran = false;
     bool local_halo = false;     // halos move by peer copies inside this process instead of NCCL
+    int stream_chunk = -1;       // frangi_gpu_run: planes per pipelined chunk; 0 = off, -1 = automatic
+    bool last_streamed = false;  // the last run recorded no per-class events
     int timing_depth = 1;        // event sets kept per slab
     long long runs_recorded = 0; // runs since the last frangi_gpu_timing_depth call
     float last_ms[8] = { 0 };
@@ -223,6 +226,9 @@ void free_slab(Slab& s)
     cudaFree(s.dGather);
     if (s.s_main) cudaStreamDestroy(s.s_main);
     if (s.s_comm) cudaStreamDestroy(s.s_comm);
+    if (s.s_h2d) cudaStreamDestroy(s.s_h2d);
+    if (s.s_d2h) cudaStreamDestroy(s.s_d2h);
+    for (auto e : s.ev_chunk) cudaEventDestroy(e);
     s = Slab();
 }
 
@@ -281,6 +287,8 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     CK(cudaSetDevice(dev));
     CK(cudaStreamCreateWithFlags(&s.s_main, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.s_d2h, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&s.ev_boundary, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_halo, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
@@ -544,6 +552,7 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
     const bool multi = H->nslabs_total > 1;
     const int ev_set = (int)(H->runs_recorded % H->timing_depth);
     H->runs_recorded++;
+    H->last_streamed = false;
     for (size_t k = 0; k < H->slabs.size(); ++k) {
         Slab& s = H->slabs[k];
         CK(cudaSetDevice(s.dev));
@@ -656,6 +665,8 @@ int sync_all(frangi_gpu* H)
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamSynchronize(s.s_main));
         CK(cudaStreamSynchronize(s.s_comm));
+        CK(cudaStreamSynchronize(s.s_h2d));
+        CK(cudaStreamSynchronize(s.s_d2h));
     }
     return 0;
 }
@@ -673,7 +684,13 @@ int collect(frangi_gpu* H, float* Jmin, float* Jmax)
     const int S = (int)H->scales.size();
     std::memset(H->last_ms, 0, sizeof H->last_ms);
     CK(cudaSetDevice(s0.dev));
-    const int nsets = (int)std::min<long long>(H->runs_recorded, H->timing_depth);
+    int nsets = (int)std::min<long long>(H->runs_recorded, H->timing_depth);
+    if (H->last_streamed) {
+        float t;
+        CK(cudaEventElapsedTime(&t, s0.ev_all[0], s0.ev_all[4 * S + 1]));
+        H->last_ms[5] = t;
+        nsets = 0;
+    }
     for (int r = 0; r < nsets; ++r) {
         const cudaEvent_t* ev = s0.ev_all.data() + (size_t)r * (4 * S + 2);
         float t;
@@ -723,6 +740,86 @@ long long local_voxels(frangi_gpu* H)
 }
 
 }  // namespace
+
+// frangi_gpu_run on one device, pipelined over z chunks: the chunk's input planes go up on
+// one stream, its three scales run on the main stream, its finished rows of J / V come down
+// on a third stream while the next chunk is being computed.  A chunk is a view of the slab
+// (own planes [cz0, cz1), smoothed planes computed locally from the resident input, so no
+// exchange); results are bit-identical to the one-piece run.  Host<->device copies overlap
+// the kernels only when the host buffers are pinned (frangi_gpu_host_alloc).
+int run_streamed(frangi_gpu* H, const uint8_t* I_host, float* J, uint8_t* Vx, uint8_t* Vy, uint8_t* Vz, uint8_t* J8,
+                 uint8_t* sc, float* dir, int ch)
+{
+    Slab& s = H->slabs[0];
+    const int S = (int)H->scales.size();
+    const int nz = s.ze - s.zb;
+    const int nch = (nz + ch - 1) / ch;
+    const size_t wh = (size_t)H->w * H->h;
+    if (sc && !s.dScale) return fail(FRANGI_GPU_ESTATE, "scale index not kept: create with FRANGI_GPU_FLAG_SCALE_IDX");
+    if (dir && !s.dDir) return fail(FRANGI_GPU_ESTATE, "float direction not kept: create with FRANGI_GPU_FLAG_DIR_F32");
+    CK(cudaSetDevice(s.dev));
+    while ((int)s.ev_chunk.size() < 2 * nch) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s.ev_chunk.push_back(e);
+    }
+    H->runs_recorded++;
+    H->last_streamed = true;
+    s.ev_time = s.ev_all.data();
+    s.hMinMax[0] = 0x7f7fffff;
+    s.hMinMax[1] = (int)0xff7fffffu;
+    CK(cudaMemcpyAsync(s.dMinMax, s.hMinMax, 2 * sizeof(int), cudaMemcpyHostToDevice, s.s_main));
+    CK(cudaEventRecord(s.ev_time[0], s.s_main));
+    int uploaded = s.zb;                      // planes [zb, uploaded) of the input are on their way
+    for (int c = 0; c < nch; ++c) {
+        const int cz0 = s.zb + c * ch, cz1 = std::min(cz0 + ch, s.ze);
+        Slab v = s;                           // shallow view: same buffers, this chunk's planes
+        v.zb = cz0; v.ze = cz1;
+        v.fb = std::max(cz0 - 2, s.zb); v.fe = std::min(cz1 + 2, s.ze);
+        const size_t off = (size_t)(cz0 - s.zb) * wh;
+        v.dJ = s.dJ + off; v.dVx = s.dVx + off; v.dVy = s.dVy + off; v.dVz = s.dVz + off;
+        if (s.dScale) v.dScale = s.dScale + off;
+        if (s.dDir) v.dDir = s.dDir + off;
+        const uint8_t* I_view = s.dI + off;
+        const int need_hi = std::min(v.fe + H->rz_max, s.ze);
+        if (need_hi > uploaded) {
+            CK(cudaMemcpyAsync(s.dI + (size_t)(uploaded - s.zb) * wh, I_host + (size_t)(uploaded - s.zb) * wh,
+                               (size_t)(need_hi - uploaded) * wh, cudaMemcpyHostToDevice, s.s_h2d));
+            uploaded = need_hi;
+        }
+        CK(cudaEventRecord(s.ev_chunk[2 * c], s.s_h2d));
+        CK(cudaStreamWaitEvent(s.s_main, s.ev_chunk[2 * c], 0));
+        for (int si = 0; si < S; ++si) {
+            const ScalePlan& sp = H->scales[si];
+            v.xb = std::max(v.fb - sp.rz, s.zb); v.xe = std::min(v.fe + sp.rz, s.ze);
+            RC(launch_xy(H, v, sp, I_view, v.xb, v.xe));
+            RC(launch_z(H, v, sp));
+            RC(launch_voxel(H, v, sp, si));
+        }
+        CK(cudaEventRecord(s.ev_chunk[2 * c + 1], s.s_main));
+        CK(cudaStreamWaitEvent(s.s_d2h, s.ev_chunk[2 * c + 1], 0));
+        const size_t n = (size_t)(cz1 - cz0) * wh;
+        if (J) CK(cudaMemcpyAsync(J + off, v.dJ, n * 4, cudaMemcpyDeviceToHost, s.s_d2h));
+        if (Vx) CK(cudaMemcpyAsync(Vx + off, v.dVx, n, cudaMemcpyDeviceToHost, s.s_d2h));
+        if (Vy) CK(cudaMemcpyAsync(Vy + off, v.dVy, n, cudaMemcpyDeviceToHost, s.s_d2h));
+        if (Vz) CK(cudaMemcpyAsync(Vz + off, v.dVz, n, cudaMemcpyDeviceToHost, s.s_d2h));
+        if (sc) CK(cudaMemcpyAsync(sc + off, v.dScale, n, cudaMemcpyDeviceToHost, s.s_d2h));
+        if (dir)
+            for (int k = 0; k < 3; ++k)
+                CK(cudaMemcpyAsync(dir + (size_t)k * s.voxels + off, v.dDir + (size_t)k * s.voxels, n * 4,
+                                   cudaMemcpyDeviceToHost, s.s_d2h));
+    }
+    // the 8-bit map needs the global min / max: after the last chunk
+    const int nb = (int)std::min<long long>((s.voxels + 255) / 256, 148 * 16);
+    j_to_j8_kernel<<<nb, 256, 0, s.s_main>>>(s.dJ, s.dJ8, s.voxels, s.dMinMax);
+    g_launches++;
+    CK(cudaGetLastError());
+    if (J8) CK(cudaMemcpyAsync(J8, s.dJ8, (size_t)s.voxels, cudaMemcpyDeviceToHost, s.s_main));
+    CK(cudaMemcpyAsync(s.hMinMax, s.dMinMax, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.s_main));
+    CK(cudaEventRecord(s.ev_time[4 * S + 1], s.s_main));
+    H->ran = true;
+    return 0;
+}
 
 // =============================== C-ABI ========================================
 
@@ -921,6 +1018,17 @@ FRANGI_API int frangi_gpu_run(frangi_gpu_t* H, const uint8_t* I_host, float* J, 
                               uint8_t* Vx, uint8_t* Vy, uint8_t* Vz, uint8_t* J8, uint8_t* sc, float* dir)
 {
     if (!H || !I_host) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    if (H->nslabs_total == 1) {
+        // one device: pipeline upload / kernels / download over z chunks when the volume is deep enough
+        const Slab& s0 = H->slabs[0];
+        const int halo = H->rz_max + 2;
+        int ch = H->stream_chunk < 0 ? std::max(32, 2 * halo) : H->stream_chunk;
+        if (ch > 0 && ch < halo) ch = halo;
+        if (ch > 0 && (s0.ze - s0.zb) >= 2 * ch) {
+            RC(run_streamed(H, I_host, J, Vx, Vy, Vz, J8, sc, dir, ch));
+            return collect(H, Jmin, Jmax);
+        }
+    }
     RC(frangi_gpu_upload(H, I_host));
     std::vector<const uint8_t*> in;
     for (auto& s : H->slabs) in.push_back(s.dI);
@@ -932,6 +1040,13 @@ FRANGI_API int frangi_gpu_run(frangi_gpu_t* H, const uint8_t* I_host, float* J, 
         off += s.voxels;
     }
     return collect(H, Jmin, Jmax);
+}
+
+FRANGI_API int frangi_gpu_set_stream_chunk(frangi_gpu_t* H, int planes)
+{
+    if (!H || planes < -1) return fail(FRANGI_GPU_EINVAL, "bad argument");
+    H->stream_chunk = planes;
+    return 0;
 }
 
 FRANGI_API int frangi_gpu_device_outputs(frangi_gpu_t* H, int slab, frangi_gpu_outputs_t* out)

@@ -55,6 +55,7 @@ SYMBOLS = {
     "frangi_gpu_nccl_unique_id": (C.c_int, [_VP]),
     "frangi_gpu_destroy": (None, [_VP]),
     "frangi_gpu_run": (C.c_int, [_VP, _VP, _VP, _f32p, _f32p, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "frangi_gpu_set_stream_chunk": (C.c_int, [_VP, C.c_int]),
     "frangi_gpu_run_device": (C.c_int, [_VP, _VP, _f32p, _f32p]),
     "frangi_gpu_upload": (C.c_int, [_VP, _VP]),
     "frangi_gpu_run_resident": (C.c_int, [_VP, _f32p, _f32p]),
@@ -247,6 +248,10 @@ class FrangiPlan:
         ms = (C.c_float * 8)()
         _check(self.lib.frangi_gpu_last_timings(self.handle, ms, 8))
         return dict(gauss_xy=ms[0], gauss_z=ms[1], hessian_eigen=ms[2], j8=ms[3], halo_wait=ms[4], total=ms[5])
+
+    def set_stream_chunk(self, planes: int):
+        """Planes per pipelined chunk of run(): 0 = one piece, -1 = automatic."""
+        _check(self.lib.frangi_gpu_set_stream_chunk(self.handle, planes))
 
     def timing_depth(self, depth: int):
         """Keep the event sets of the last `depth` runs; timings() then returns their mean."""

@@ -56,3 +56,24 @@ def test_slabs_over_real_devices_nccl_and_peer_copies():
         assert many["Jmax"] == one["Jmax"]
         for k in KEYS:
             assert np.array_equal(one[k], many[k]), (devs, fl, k)
+
+
+@pytest.mark.parametrize("chunk", [11, 16, 24])
+def test_pipelined_run_equals_one_piece_run(chunk):
+    """frangi_gpu_run pipelines copies and kernels over z chunks; the chunks are views of the slab
+    and must give the one-piece result bit for bit (J, V, J8, Jmin, Jmax, extras)."""
+    I = make_volume(150, 70, 48, seed=35, n_neurites=6)
+    sigs = [2.0, 4.0, 6.0]
+    flags = FLAG_DIR_F32 | FLAG_SCALE_IDX
+    l, h, w = I.shape
+    p = FrangiPlan(sigs, 2.0, .5, .5, 500., False, w, h, l, flags=flags)
+    p.set_stream_chunk(0)
+    one = p.run(I, want_J8=True)
+    p.set_stream_chunk(chunk)
+    before = pnr_b200.launch_count()
+    many = p.run(I, want_J8=True)
+    assert pnr_b200.launch_count() - before > 3 * 4 + 1, "the chunked path should launch per chunk"
+    p.close()
+    assert many["Jmin"] == one["Jmin"] and many["Jmax"] == one["Jmax"]
+    for k in KEYS:
+        assert np.array_equal(one[k], many[k]), k
