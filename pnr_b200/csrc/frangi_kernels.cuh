@@ -104,37 +104,61 @@ gauss_xy_kernel(const __grid_constant__ XYParams p, const __grid_constant__ Gaus
     const int xr = tid & 15;   // x pass: row within the batch
     const int xc = tid >> 4;   // x pass: 16-column chunk
     const int nb = (ye - ys + C::RB - 1) / C::RB;
-    int phase = 0;             // x-pass phases done; phase m covers rows ys - L + m*RB + [0, RB)
+    const int nphases = nb + C::NBLK - 1;   // x-pass phases; phase m covers rows ys - L + m*RB + [0, RB)
 
-    for (int b = 0; b < nb; ++b) {
-        const int need = b + C::NBLK;
-        while (phase < need) {
-            __syncthreads();  // s_in and the ring block about to be overwritten are no longer read
-            // ---- stage RB input rows as float ----
-            const int r0 = ys - L + phase * C::RB;
-            constexpr int GROUPS = C::PIN0 / 4;
-            for (int idx = tid; idx < C::RB * GROUPS; idx += C::NT) {
+    // Input staging is software-pipelined: the raw bytes of phase m+1 (4 pixels per 32-bit word,
+    // replicate-clamped) are loaded into registers while phase m is being filtered, and are
+    // converted to float in shared memory at the top of phase m+1.
+    constexpr int GROUPS = C::PIN0 / 4;
+    constexpr int NW = (C::RB * GROUPS + C::NT - 1) / C::NT;   // words per thread per phase
+    uint32_t raw[NW];
+    auto fetch = [&](int ph) {
+        const int r0 = ys - L + ph * C::RB;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            const int idx = tid + k * C::NT;
+            uint32_t u = 0;
+            if (idx < C::RB * GROUPS) {
                 const int r = idx / GROUPS;
                 const int g = idx - r * GROUPS;
                 const int y = clampi(r0 + r, 0, p.h - 1);
                 const int xg = x0 - C::LAL + 4 * g;
                 const uint8_t* row = Iz + (long long)y * p.w;
-                float4 v;
                 if (p.vec_ok && xg >= 0 && xg + 3 < p.w) {
-                    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(row + xg));
+                    u = __ldg(reinterpret_cast<const uint32_t*>(row + xg));
+                } else {
+                    u = (uint32_t)__ldg(row + clampi(xg + 0, 0, p.w - 1)) |
+                        ((uint32_t)__ldg(row + clampi(xg + 1, 0, p.w - 1)) << 8) |
+                        ((uint32_t)__ldg(row + clampi(xg + 2, 0, p.w - 1)) << 16) |
+                        ((uint32_t)__ldg(row + clampi(xg + 3, 0, p.w - 1)) << 24);
+                }
+            }
+            raw[k] = u;
+        }
+    };
+    fetch(0);
+
+    for (int phase = 0; phase < nphases; ++phase) {
+        {
+            __syncthreads();  // s_in and the ring block about to be overwritten are no longer read
+            // ---- stage RB input rows as float ----
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                const int idx = tid + k * C::NT;
+                if (idx < C::RB * GROUPS) {
+                    const int r = idx / GROUPS;
+                    const int g = idx - r * GROUPS;
+                    const uint32_t u = raw[k];
+                    float4 v;
                     v.x = (float)(u & 0xffu);
                     v.y = (float)((u >> 8) & 0xffu);
                     v.z = (float)((u >> 16) & 0xffu);
                     v.w = (float)(u >> 24);
-                } else {
-                    v.x = (float)__ldg(row + clampi(xg + 0, 0, p.w - 1));
-                    v.y = (float)__ldg(row + clampi(xg + 1, 0, p.w - 1));
-                    v.z = (float)__ldg(row + clampi(xg + 2, 0, p.w - 1));
-                    v.w = (float)__ldg(row + clampi(xg + 3, 0, p.w - 1));
+                    *reinterpret_cast<float4*>(s_in + r * C::PIN + 4 * g) = v;
                 }
-                *reinterpret_cast<float4*>(s_in + r * C::PIN + 4 * g) = v;
             }
             __syncthreads();
+            if (phase + 1 < nphases) fetch(phase + 1);   // in flight during the x and y passes below
             // ---- x pass: 16 outputs of row xr, columns 16*xc .. 16*xc+15 ----
             {
                 float acc[16];
@@ -162,8 +186,9 @@ gauss_xy_kernel(const __grid_constant__ XYParams p, const __grid_constant__ Gaus
                 dst[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
                 dst[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
             }
-            ++phase;
         }
+        const int b = phase - (C::NBLK - 1);     // the batch whose 16 + 2L ring rows are now complete
+        if (b < 0) continue;
         __syncthreads();
         // ---- y pass: column tid, output rows ys + b*RB + [0, RB) ----
         {
