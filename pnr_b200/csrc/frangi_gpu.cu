@@ -405,11 +405,11 @@ FrangiConsts make_consts(frangi_gpu* H, float sigma2)
     return k;
 }
 
-template <int MODE>
+template <int MODE, bool BRIGHT = false>
 int launch_voxel_t(const VoxelParams& p, long long nblocks, long long nshell, cudaStream_t st)
 {
     if (nblocks > 0) {
-        auto k = hessian_eigen_kernel<MODE>;
+        auto k = hessian_eigen_kernel<MODE, BRIGHT>;
         static thread_local int configured_dev[64] = { 0 };
         int dev = 0;
         CK(cudaGetDevice(&dev));
@@ -477,6 +477,7 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
     if (nblocks > 0x7fffffffLL || (nshell + 127) / 128 > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
     if (D) return launch_voxel_t<2>(p, nblocks, nshell, s.s_main);
     if (si == 0) return launch_voxel_t<0>(p, nblocks, nshell, s.s_main);
+    if (!H->blackwhite) return launch_voxel_t<1, true>(p, nblocks, nshell, s.s_main);
     return launch_voxel_t<1>(p, nblocks, nshell, s.s_main);
 }
 

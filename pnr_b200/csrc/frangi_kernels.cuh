@@ -418,6 +418,7 @@ __device__ __noinline__ Hess hessian_at_face(const Field& f, int x, int y, int z
 // Outputs are dense over the slab's own planes [z_begin, z_begin + nz).
 // MODE 0: first scale, store unconditionally (frangi.cpp:234-252);
 // MODE 1: later scale, overwrite only on a strictly greater response (:254-271);
+//         BRIGHT = true adds the shortcut ordering for bright ridges (frangi_voxel_math.cuh);
 // MODE 2: stage dump of the six second differences (hessian3d parity).
 // minmax[0] = bits of min J (taken on the first scale),
 // minmax[1] = bits of max J (taken on the last scale).  J >= 0, so the int
@@ -495,7 +496,7 @@ __device__ __noinline__ float voxel_update(const VoxelParams& p, long long i, co
     return jold;
 }
 
-template <int MODE>
+template <int MODE, bool BRIGHT = false>
 __global__ void __launch_bounds__(HessTile::NT, HESS_MIN_CTAS)
 hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
 {
@@ -621,8 +622,11 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
                     Hxx[g] = DD(PAIR(b, j + 4), f0, PAIR(b, j));
                     Hyy[g] = DD(PAIR(u2, j), f0, PAIR(t2, j));
                     Hzz[g] = DD(PAIR(l2, j), f0, PAIR(k2, j));
-                    Hxy[g] = DX(PAIR(c, j + 3), PAIR(c, j + 1), PAIR(a, j + 3), PAIR(a, j + 1));
-                    Hxz[g] = DX(PAIR(nn, j + 3), PAIR(nn, j + 1), PAIR(mm, j + 3), PAIR(mm, j + 1));
+                    // the x+-1 taps sit at odd register offsets of the 128-bit loads: scalar form, no re-pairing moves
+                    Hxy[g].x = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 3], c[j + 1]), __fsub_rn(a[j + 3], a[j + 1])), qs);
+                    Hxy[g].y = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 4], c[j + 2]), __fsub_rn(a[j + 4], a[j + 2])), qs);
+                    Hxz[g].x = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 3], nn[j + 1]), __fsub_rn(mm[j + 3], mm[j + 1])), qs);
+                    Hxz[g].y = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 4], nn[j + 2]), __fsub_rn(mm[j + 4], mm[j + 2])), qs);
                     Hyz[g] = DX(PAIR(nd, j), PAIR(nu, j), PAIR(md, j), PAIR(mu, j));
                 }
 #undef PAIR
@@ -660,8 +664,8 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
             for (int g = 0; g < 2; ++g) {
                 const int j = 2 * g;
                 Eig3x2 e;
-                eig_sym3<float2>(Hxx[g], Hxy[g], Hxz[g], Hyy[g], Hyz[g], Hzz[g], e);
-                const float2 v = vesselness<float2>(e, p.k);
+                eig_sym3<float2, BRIGHT>(Hxx[g], Hxy[g], Hxz[g], Hyy[g], Hyz[g], Hzz[g], e);
+                const float2 v = vesselness<float2, BRIGHT>(e, p.k);
                 wr[j] = MODE == 0 || v.x > jold[j];
                 wr[j + 1] = MODE == 0 || v.y > jold[j + 1];
                 jn[j] = wr[j] ? v.x : jold[j];

@@ -79,6 +79,7 @@ template <class V> __device__ __forceinline__ V vdiff(V a, V b, V c, V d) { retu
 template <class V> struct EigT {
     V l1, l2, l3;   // |l1| <= |l2| <= |l3| with the reference's tie rules
     V vx, vy, vz;   // unit eigenvector of l1
+    bool zero[2];   // BRIGHT_LATER only: the sign gate of frangi.cpp:225-228 closes (response is 0)
 };
 typedef EigT<float> Eig3;
 typedef EigT<float2> Eig3x2;
@@ -108,7 +109,14 @@ __device__ __noinline__ Eig3 eig_diag(float a00, float a11, float a22)
     return out;
 }
 
-template <class V>
+// BRIGHT_LATER: a later scale of a bright-ridge run (blackwhite == false, frangi.cpp:254-271).
+// There a voxel can only be overwritten when its response is positive, i.e. when the two
+// eigenvalues of largest magnitude are <= 0; for the ascending triple e0 <= e1 <= e2 that is
+//   e1 <= 0  and  (e2 <= 0  or  (|e2| <= |e1| and |e2| < |e0|))            (tie rules of :1289-1304)
+// and then the |lambda| order is simply (l1, l2, l3) = (e2, e1, e0) with the direction the
+// eigenvector of the LARGEST eigenvalue.  Voxels that fail the test are flagged `zero` (their
+// response is 0 and never wins), so the general ordering logic is not needed.
+template <class V, bool BRIGHT_LATER = false>
 __device__ __forceinline__ void eig_sym3(V a00, V a01, V a02, V a11, V a12, V a22, EigT<V>& out)
 {
     typedef Lanes<V> L;
@@ -130,8 +138,8 @@ __device__ __forceinline__ void eig_sym3(V a00, V a01, V a02, V a11, V a12, V a2
     for (int k = 0; k < L::N; ++k) {
         const float h = L::get(hd, k), pk = L::get(p, k);
         L::set(ar, k, fminf(fabsf(h), 1.0f));
-        top[k] = h >= 0.0f;                    // the largest eigenvalue is the isolated one
-        L::set(sp, k, top[k] ? pk : -pk);
+        top[k] = !signbit(h);                  // the largest eigenvalue is the isolated one
+        L::set(sp, k, copysignf(pk, h));
     }
     V g = vfma(ar, L::bc(-0.00202751093f), L::bc(0.0100089306f));
     g = vfma(ar, g, L::bc(-0.0248566089f));
@@ -191,9 +199,20 @@ __device__ __forceinline__ void eig_sym3(V a00, V a01, V a02, V a11, V a12, V a2
 #pragma unroll
     for (int k = 0; k < L::N; ++k) L::set(disc, k, mufu_sqrt(L::get(d2, k)));
     const V la = vsub(mean, disc), lb = vadd(mean, disc);
+    bool sel_i[L::N];
+    if (BRIGHT_LATER) {
+#pragma unroll
+        for (int k = 0; k < L::N; ++k) {
+            const float fa = L::get(la, k), fb = L::get(lb, k), fi = L::get(lam, k);
+            const float e0 = top[k] ? fa : fi, e1 = top[k] ? fb : fa, e2 = top[k] ? fi : fb;
+            const bool pass = e1 <= 0.0f && (e2 <= 0.0f || (fabsf(e2) <= fabsf(e1) && fabsf(e2) < fabsf(e0)));
+            out.zero[k] = !pass;
+            L::set(out.l1, k, e2); L::set(out.l2, k, e1); L::set(out.l3, k, e0);
+            sel_i[k] = top[k];
+        }
+    } else {
     // |lambda| order with the reference's rules, applied to the ascending triple
     // (la, lb, lam) if top else (lam, la, lb); sel_i: column 0 is the isolated eigenvector
-    bool sel_i[L::N];
 #pragma unroll
     for (int k = 0; k < L::N; ++k) {
         const float fa = L::get(la, k), fb = L::get(lb, k), fi = L::get(lam, k);
@@ -209,6 +228,7 @@ __device__ __forceinline__ void eig_sym3(V a00, V a01, V a02, V a11, V a12, V a2
         L::set(out.l2, k, sw ? x : y);
         // where the isolated eigenvalue went: it is e2 if top (x when c1, y when c2), else e0 (x unless c1)
         sel_i[k] = top[k] ? ((c1 && !sw) || (c2 && sw)) : (!c1 && !sw);
+    }
     }
     // null vector of (M - l1 I) in (u, w) coordinates, from the larger row
     const V f0 = vsub(m00, out.l1), f1 = vsub(m11, out.l1);
@@ -233,12 +253,17 @@ __device__ __forceinline__ void eig_sym3(V a00, V a01, V a02, V a11, V a12, V a2
         L::set(out.vz, k, sel_i[k] ? L::get(iz, k) : L::get(pz, k));
     }
     // exactly diagonal inputs follow the reference's conventions (rare outside flat background)
+    float offmin = L::get(off, 0);
+#pragma unroll
+    for (int k = 1; k < L::N; ++k) offmin = fminf(offmin, L::get(off, k));
+    if (offmin == 0.0f)
 #pragma unroll
     for (int k = 0; k < L::N; ++k)
         if (L::get(off, k) == 0.0f) {
             const Eig3 e = eig_diag(L::get(a00, k), L::get(a11, k), L::get(a22, k));
             L::set(out.l1, k, e.l1); L::set(out.l2, k, e.l2); L::set(out.l3, k, e.l3);
             L::set(out.vx, k, e.vx); L::set(out.vy, k, e.vy); L::set(out.vz, k, e.vz);
+            if (BRIGHT_LATER) out.zero[k] = e.l2 > 0.0f || e.l3 > 0.0f;
         }
 }
 
@@ -273,7 +298,7 @@ __device__ __forceinline__ V one_minus_exp_neg(V x)
 }
 
 // Frangi vesselness from |lambda|-sorted eigenvalues (frangi.cpp:206-231).
-template <class V>
+template <class V, bool BRIGHT_LATER = false>
 __device__ __forceinline__ V vesselness(const EigT<V>& e, const FrangiConsts& c)
 {
     typedef Lanes<V> L;
@@ -287,7 +312,12 @@ __device__ __forceinline__ V vesselness(const EigT<V>& e, const FrangiConsts& c)
     const V Ra2 = vmul(ra, ra);
     const V Rb2 = vmul(a11, i23);                                            // (|l1| / sqrt(|l2 l3|))^2
     const V S2 = vfma(a2, a2, vfma(a3, a3, a11));
-    const V tRa = one_minus_exp_neg<V, false>(vmul(Ra2, L::bc(c.inv_2a2)));
+    // 1 - exp(-Ra^2/2a^2) straight from ex2: its absolute error (1e-7) is multiplied by tS, which is
+    // orders of magnitude inside the 1e-6 absolute tolerance, and where J is strong this term is O(1)
+    const V xa = vmul(Ra2, L::bc(-1.4426950408889634f * c.inv_2a2));
+    V tRa;
+#pragma unroll
+    for (int k = 0; k < L::N; ++k) L::set(tRa, k, 1.0f - mufu_ex2(L::get(xa, k)));
     const V xb = vmul(Rb2, L::bc(-1.4426950408889634f * c.inv_2b2));
     V tRb;
 #pragma unroll
@@ -298,9 +328,10 @@ __device__ __forceinline__ V vesselness(const EigT<V>& e, const FrangiConsts& c)
     for (int k = 0; k < L::N; ++k) {
         const float l2 = L::get(e.l2, k), l3 = L::get(e.l3, k);
         float vk = L::get(v, k);
-        const bool gate = c.blackwhite ? (l2 < 0.0f || l3 < 0.0f) : (l2 > 0.0f || l3 > 0.0f);   // frangi.cpp:221-228
-        if (gate || !(vk == vk)) vk = 0.0f;              // NaN (0/0 on a zero Hessian) -> 0, frangi.cpp:231
-        L::set(v, k, vk);
+        vk = fmaxf(vk, 0.0f);                            // NaN (0/0 on a zero Hessian) -> 0, frangi.cpp:231
+        const bool gate = BRIGHT_LATER ? e.zero[k]
+                                       : (c.blackwhite ? fminf(l2, l3) < 0.0f : fmaxf(l2, l3) > 0.0f);   // frangi.cpp:221-228
+        L::set(v, k, gate ? 0.0f : vk);
     }
     return v;
 }
@@ -309,7 +340,7 @@ __device__ __forceinline__ V vesselness(const EigT<V>& e, const FrangiConsts& c)
 // c*127.5 + 128 lies in (0.49, 255.51) and its floor is a byte; NaN converts to 0
 __device__ __forceinline__ uint32_t dir_code(float c)
 {
-    return (uint32_t)min(__float2int_rd(fmaf(c, 127.5f, 128.0f)), 255) & 0xffu;
+    return (uint32_t)__float2int_rd(fmaf(c, 127.5f, 128.0f)) & 0xffu;
 }
 
 }  // namespace frangi
