@@ -477,8 +477,23 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
     if (nblocks > 0x7fffffffLL || (nshell + 127) / 128 > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
     if (D) return launch_voxel_t<2>(p, nblocks, nshell, s.s_main);
     if (si == 0) return launch_voxel_t<0>(p, nblocks, nshell, s.s_main);
-    if (!H->blackwhite) return launch_voxel_t<1, true>(p, nblocks, nshell, s.s_main);
-    return launch_voxel_t<1>(p, nblocks, nshell, s.s_main);
+    if (H->blackwhite) return launch_voxel_t<1>(p, nblocks, nshell, s.s_main);
+    if (p.zchunk >= (1 << 20)) return launch_voxel_t<1, true>(p, nblocks, nshell, s.s_main);   // packed z offset has 20 bits
+    // later scale of a bright-ridge run: the compacting kernel, then the shell
+    if (nblocks > 0) {
+        constexpr int smem = HessTile::SMEM_BYTES + HessQueue::BYTES;
+        static thread_local int configured_dev[64] = { 0 };
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        if (dev < 64 && !configured_dev[dev]) {
+            CK(cudaFuncSetAttribute(hessian_eigen_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured_dev[dev] = 1;
+        }
+        hessian_eigen_compact_kernel<<<(unsigned)nblocks, HessTile::NT, smem, s.s_main>>>(p);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
+    return launch_voxel_t<1>(p, 0, nshell, s.s_main);
 }
 
 // Exchange the xy-smoothed boundary planes of every local slab with its z

@@ -421,7 +421,7 @@ __device__ __noinline__ Hess hessian_at_face(const Field& f, int x, int y, int z
 //         BRIGHT = true adds the shortcut ordering for bright ridges (frangi_voxel_math.cuh);
 // MODE 2: stage dump of the six second differences (hessian3d parity).
 // minmax[0] = bits of min J (taken on the first scale),
-// minmax[1] = bits of max J (taken on the last scale).  J >= 0, so the int
+// minmax[1] = bits of max J (max over every value any scale leaves in J).  J >= 0, so the int
 // order of the bit patterns is the float order.
 // ---------------------------------------------------------------------------
 struct FView {
@@ -494,6 +494,71 @@ __device__ __noinline__ float voxel_update(const VoxelParams& p, long long i, co
         return v;
     }
     return jold;
+}
+
+// Second differences of four consecutive x voxels of one tile row, interior form, as two packed
+// pairs (voxels 0,1 and 2,3).  `o` = tile entry of (x - 2, y) of the first voxel; P0 = plane z,
+// Pm1/Pp1 = z-+1, Pm2/Pp2 = z-+2 of the shared-memory ring.
+__device__ __forceinline__ void quad_hessians(const float* P0, const float* Pm1, const float* Pp1, const float* Pm2,
+                                              const float* Pp2, int o, float qs, float2* Hxx, float2* Hxy,
+                                              float2* Hxz, float2* Hyy, float2* Hyz, float2* Hzz)
+{
+    using T = HessTile;
+                    // plane z: rows y-1, y, y+1 over x-2 .. x+5; rows y-2, y+2 over x .. x+3
+                    float a[8], b[8], c[8];
+                    *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(P0 + o - T::PW);
+                    *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(P0 + o - T::PW + 4);
+                    *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(P0 + o);
+                    *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(P0 + o + 4);
+                    *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(P0 + o + T::PW);
+                    *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(P0 + o + T::PW + 4);
+                    float t2[4], u2[4];
+                    *reinterpret_cast<float2*>(t2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 2);
+                    *reinterpret_cast<float2*>(t2 + 2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 4);
+                    *reinterpret_cast<float2*>(u2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 2);
+                    *reinterpret_cast<float2*>(u2 + 2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 4);
+                    float k2[4], l2[4];
+                    *reinterpret_cast<float2*>(k2) = *reinterpret_cast<const float2*>(Pm2 + o + 2);
+                    *reinterpret_cast<float2*>(k2 + 2) = *reinterpret_cast<const float2*>(Pm2 + o + 4);
+                    *reinterpret_cast<float2*>(l2) = *reinterpret_cast<const float2*>(Pp2 + o + 2);
+                    *reinterpret_cast<float2*>(l2 + 2) = *reinterpret_cast<const float2*>(Pp2 + o + 4);
+                    // planes z-1, z+1: row y over x-1 .. x+4 (loaded as x-2 .. x+5), rows y-1, y+1 over x .. x+3
+                    float mm[8], nn[8], mu[4], md[4], nu[4], nd[4];
+                    *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(Pm1 + o);
+                    *reinterpret_cast<float4*>(mm + 4) = *reinterpret_cast<const float4*>(Pm1 + o + 4);
+                    *reinterpret_cast<float4*>(nn) = *reinterpret_cast<const float4*>(Pp1 + o);
+                    *reinterpret_cast<float4*>(nn + 4) = *reinterpret_cast<const float4*>(Pp1 + o + 4);
+                    *reinterpret_cast<float2*>(mu) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 2);
+                    *reinterpret_cast<float2*>(mu + 2) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 4);
+                    *reinterpret_cast<float2*>(md) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 2);
+                    *reinterpret_cast<float2*>(md + 2) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 4);
+                    *reinterpret_cast<float2*>(nu) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 2);
+                    *reinterpret_cast<float2*>(nu + 2) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 4);
+                    *reinterpret_cast<float2*>(nd) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 2);
+                    *reinterpret_cast<float2*>(nd + 2) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 4);
+                    const float2 qs2 = make_float2(qs, qs);
+                    // (hi - mid) - (mid - lo), then * sigma^2/4: FADD2 / FMUL2 round each lane exactly like
+                    // the scalar __fsub_rn / __fmul_rn chain (no multiply feeds an add, so nothing can fuse)
+    #define PAIR(arr, i) make_float2((arr)[(i)], (arr)[(i) + 1])
+    #define DD(hi, mid, lo) vmul(vsub(vsub(hi, mid), vsub(mid, lo)), qs2)
+    #define DX(hi1, lo1, hi0, lo0) vmul(vsub(vsub(hi1, lo1), vsub(hi0, lo0)), qs2)
+    #pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int j = 2 * g;
+                        const float2 f0 = PAIR(b, j + 2);
+                        Hxx[g] = DD(PAIR(b, j + 4), f0, PAIR(b, j));
+                        Hyy[g] = DD(PAIR(u2, j), f0, PAIR(t2, j));
+                        Hzz[g] = DD(PAIR(l2, j), f0, PAIR(k2, j));
+                        // the x+-1 taps sit at odd register offsets of the 128-bit loads: scalar form, no re-pairing moves
+                        Hxy[g].x = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 3], c[j + 1]), __fsub_rn(a[j + 3], a[j + 1])), qs);
+                        Hxy[g].y = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 4], c[j + 2]), __fsub_rn(a[j + 4], a[j + 2])), qs);
+                        Hxz[g].x = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 3], nn[j + 1]), __fsub_rn(mm[j + 3], mm[j + 1])), qs);
+                        Hxz[g].y = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 4], nn[j + 2]), __fsub_rn(mm[j + 4], mm[j + 2])), qs);
+                        Hyz[g] = DX(PAIR(nd, j), PAIR(nu, j), PAIR(md, j), PAIR(mu, j));
+                    }
+    #undef PAIR
+    #undef DD
+    #undef DX
 }
 
 template <int MODE, bool BRIGHT = false>
@@ -575,64 +640,7 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
             if (y < 2 || y > h - 3 || !any_x) continue;
             // second differences of the quad as two packed pairs (voxels 0,1 and 2,3)
             float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
-            {
-                const int o = (yl + 2) * T::PW + 4 * tx;      // tile entry of (x = xq - 2, y)
-                // plane z: rows y-1, y, y+1 over x-2 .. x+5; rows y-2, y+2 over x .. x+3
-                float a[8], b[8], c[8];
-                *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(P0 + o - T::PW);
-                *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(P0 + o - T::PW + 4);
-                *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(P0 + o);
-                *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(P0 + o + 4);
-                *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(P0 + o + T::PW);
-                *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(P0 + o + T::PW + 4);
-                float t2[4], u2[4];
-                *reinterpret_cast<float2*>(t2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 2);
-                *reinterpret_cast<float2*>(t2 + 2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 4);
-                *reinterpret_cast<float2*>(u2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 2);
-                *reinterpret_cast<float2*>(u2 + 2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 4);
-                float k2[4], l2[4];
-                *reinterpret_cast<float2*>(k2) = *reinterpret_cast<const float2*>(Pm2 + o + 2);
-                *reinterpret_cast<float2*>(k2 + 2) = *reinterpret_cast<const float2*>(Pm2 + o + 4);
-                *reinterpret_cast<float2*>(l2) = *reinterpret_cast<const float2*>(Pp2 + o + 2);
-                *reinterpret_cast<float2*>(l2 + 2) = *reinterpret_cast<const float2*>(Pp2 + o + 4);
-                // planes z-1, z+1: row y over x-1 .. x+4 (loaded as x-2 .. x+5), rows y-1, y+1 over x .. x+3
-                float mm[8], nn[8], mu[4], md[4], nu[4], nd[4];
-                *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(Pm1 + o);
-                *reinterpret_cast<float4*>(mm + 4) = *reinterpret_cast<const float4*>(Pm1 + o + 4);
-                *reinterpret_cast<float4*>(nn) = *reinterpret_cast<const float4*>(Pp1 + o);
-                *reinterpret_cast<float4*>(nn + 4) = *reinterpret_cast<const float4*>(Pp1 + o + 4);
-                *reinterpret_cast<float2*>(mu) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 2);
-                *reinterpret_cast<float2*>(mu + 2) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 4);
-                *reinterpret_cast<float2*>(md) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 2);
-                *reinterpret_cast<float2*>(md + 2) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 4);
-                *reinterpret_cast<float2*>(nu) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 2);
-                *reinterpret_cast<float2*>(nu + 2) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 4);
-                *reinterpret_cast<float2*>(nd) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 2);
-                *reinterpret_cast<float2*>(nd + 2) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 4);
-                const float2 qs2 = make_float2(qs, qs);
-                // (hi - mid) - (mid - lo), then * sigma^2/4: FADD2 / FMUL2 round each lane exactly like
-                // the scalar __fsub_rn / __fmul_rn chain (no multiply feeds an add, so nothing can fuse)
-#define PAIR(arr, i) make_float2((arr)[(i)], (arr)[(i) + 1])
-#define DD(hi, mid, lo) vmul(vsub(vsub(hi, mid), vsub(mid, lo)), qs2)
-#define DX(hi1, lo1, hi0, lo0) vmul(vsub(vsub(hi1, lo1), vsub(hi0, lo0)), qs2)
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int j = 2 * g;
-                    const float2 f0 = PAIR(b, j + 2);
-                    Hxx[g] = DD(PAIR(b, j + 4), f0, PAIR(b, j));
-                    Hyy[g] = DD(PAIR(u2, j), f0, PAIR(t2, j));
-                    Hzz[g] = DD(PAIR(l2, j), f0, PAIR(k2, j));
-                    // the x+-1 taps sit at odd register offsets of the 128-bit loads: scalar form, no re-pairing moves
-                    Hxy[g].x = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 3], c[j + 1]), __fsub_rn(a[j + 3], a[j + 1])), qs);
-                    Hxy[g].y = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 4], c[j + 2]), __fsub_rn(a[j + 4], a[j + 2])), qs);
-                    Hxz[g].x = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 3], nn[j + 1]), __fsub_rn(mm[j + 3], mm[j + 1])), qs);
-                    Hxz[g].y = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 4], nn[j + 2]), __fsub_rn(mm[j + 4], mm[j + 2])), qs);
-                    Hyz[g] = DX(PAIR(nd, j), PAIR(nu, j), PAIR(md, j), PAIR(mu, j));
-                }
-#undef PAIR
-#undef DD
-#undef DX
-            }
+            quad_hessians(P0, Pm1, Pp1, Pm2, Pp2, (yl + 2) * T::PW + 4 * tx, qs, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
 
             const long long i0 = ((long long)(z - p.z_begin) * h + y) * w + xq;
             if (MODE == 2 || !all_x) {            // stage dump; quads that straddle an x face; unaligned widths
@@ -713,11 +721,191 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
         for (int s = 16; s > 0; s >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, s));
         if (tx == 0 && vmin < 3.0e38f) atomicMin(p.minmax + 0, __float_as_int(vmin));
     }
-    if (p.last_scale) {
+    {
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
         if (tx == 0) atomicMax(p.minmax + 1, __float_as_int(vmax));
     }
+}
+
+// K3a', later scales of a bright-ridge run (the common case: blackwhite == false,
+// frangi.cpp:254-271): the same z-marching tile, but only voxels that can still win go through
+// the eigen stage.  A voxel is overwritten only when its response is positive, which needs the
+// two eigenvalues of largest magnitude to be <= 0; by Ky Fan's inequality the sum of any two
+// diagonal entries is then <= e1 + e2 <= 0, so  Dxx+Dyy > 0 | Dxx+Dzz > 0 | Dyy+Dzz > 0  proves
+// the response is 0 (three adds, before any eigen work; ~80 % of the voxels of a neuron volume).
+// Phase A (all threads): second differences of the thread's quad, the test, survivors appended
+// (warp-aggregated atomics) to a shared-memory queue of {6 second differences, packed voxel
+// coordinate}.  Phase B: whenever the queue holds a full batch (2 entries per thread) every
+// thread takes two entries through the packed eigen stage and updates J / V where the response
+// beats the stored one, so the expensive stage always runs with full lanes.  The queue persists
+// across planes and is flushed at the end of the chunk.
+struct HessQueue {
+    static constexpr int BATCH = 2 * HessTile::NT;                                   // 512 entries
+    static constexpr int HALF = HessTile::TX * HessTile::TY / HessTile::RPT;           // appended between drains
+    static constexpr int CAP = BATCH + HALF;                                           // leftover < BATCH, plus one half plane
+    static constexpr int BYTES = CAP * 7 * 4;
+};
+
+__global__ void __launch_bounds__(HessTile::NT, 2)
+hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
+{
+    using T = HessTile;
+    using Q = HessQueue;
+    extern __shared__ __align__(16) float ring[];
+    float* q_h = ring + T::SLOTS * T::PLANE;               // 6 arrays of CAP floats
+    int* q_pos = reinterpret_cast<int*>(q_h + 6 * Q::CAP);
+    __shared__ int s_count;
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    int bid = blockIdx.x;
+    const int bx = bid % p.ntx; bid /= p.ntx;
+    const int by = bid % p.nty;
+    const int bz = bid / p.nty;
+    const int x0 = bx * T::TX - 2, y0 = by * T::TY - 2;
+    const int w = p.f.w, h = p.f.h, l = p.f.l;
+    const int zs = max(p.z_begin + bz * p.zchunk, 2);
+    const int ze = min(min(p.z_begin + (bz + 1) * p.zchunk, p.z_begin + p.nz), l - 2);
+    if (zs >= ze) return;
+    if (tid == 0) s_count = 0;
+
+    constexpr int UNITS = T::PLANE / 2, UPR = T::PW / 2;
+    constexpr int NU = (UNITS + T::NT - 1) / T::NT;
+    int g_off[NU];
+    unsigned ok_mask = 0;
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+        const int e = tid + k * T::NT;
+        const int r = e / UPR, c = 2 * (e - r * UPR);
+        const int gy = y0 + r, gx = x0 + c;
+        const bool ok = e < UNITS && gy >= 0 && gy < h && gx >= 0 && gx < w;
+        g_off[k] = ok ? gy * p.f.fpitch + gx : 0;
+        ok_mask |= (ok ? 1u : 0u) << k;
+    }
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    auto fetch = [&](int plane) {
+        const float* __restrict__ src = p.f.F + (long long)(plane - p.f.base) * p.f.fplane;
+        const unsigned dst = ring_s + ((plane % T::SLOTS) * T::PLANE + 2 * tid) * 4;
+#pragma unroll
+        for (int k = 0; k < NU; ++k)
+            if (tid + k * T::NT < UNITS) {
+                const int nbytes = (ok_mask >> k) & 1u ? 8 : 0;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + k * T::NT * 8),
+                             "l"(src + g_off[k]), "r"(nbytes) : "memory");
+            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int q = zs - 2; q <= zs + 2; ++q) fetch(q);
+
+    const int xq = bx * T::TX + 4 * tx;
+    bool m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = xq + j >= 2 && xq + j <= w - 3;
+    const bool any_x = m[0] || m[1] || m[2] || m[3];
+    const float qs = 0.25f * p.k.sigma2;
+    float vmax = 0.0f;
+
+    // Phase B on entries [first, first + count): two per thread
+    auto drain = [&](int first, int count) {
+        const int e0 = first + 2 * tid;
+        if (2 * tid >= count) return;
+        const bool two = 2 * tid + 1 < count;
+        const int e1 = two ? e0 + 1 : e0;
+        Eig3x2 e;
+        eig_sym3<float2, true>(make_float2(q_h[e0], q_h[e1]), make_float2(q_h[Q::CAP + e0], q_h[Q::CAP + e1]),
+                               make_float2(q_h[2 * Q::CAP + e0], q_h[2 * Q::CAP + e1]),
+                               make_float2(q_h[3 * Q::CAP + e0], q_h[3 * Q::CAP + e1]),
+                               make_float2(q_h[4 * Q::CAP + e0], q_h[4 * Q::CAP + e1]),
+                               make_float2(q_h[5 * Q::CAP + e0], q_h[5 * Q::CAP + e1]), e);
+        const float2 v = vesselness<float2, true>(e, p.k);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (k == 1 && !two) break;
+            const int pos = q_pos[k ? e1 : e0];              // (z - zs) << 11 | row << 7 | column
+            const int x = bx * T::TX + (pos & 127), y = by * T::TY + ((pos >> 7) & 15), z = zs + (pos >> 11);
+            const long long i = ((long long)(z - p.z_begin) * h + y) * w + x;
+            const float vk = k ? v.y : v.x;
+            if (vk > p.J[i]) {
+                p.J[i] = vk;
+                p.Vx[i] = (uint8_t)dir_code(k ? e.vx.y : e.vx.x);
+                p.Vy[i] = (uint8_t)dir_code(k ? e.vy.y : e.vy.x);
+                p.Vz[i] = (uint8_t)dir_code(k ? e.vz.y : e.vz.x);
+                if (p.scale_idx) p.scale_idx[i] = (uint8_t)p.scale;
+                if (p.dir) {
+                    p.dir[i] = k ? e.vx.y : e.vx.x;
+                    p.dir[p.voxels + i] = k ? e.vy.y : e.vy.x;
+                    p.dir[2 * p.voxels + i] = k ? e.vz.y : e.vz.x;
+                }
+                vmax = fmaxf(vmax, vk);
+            }
+        }
+    };
+
+    for (int z = zs; z < ze; ++z) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                          // plane z+2 visible; plane z-3's slot and the queue count are settled
+        if (z + 1 < ze) fetch(z + 3);
+        const float* P0 = ring + (z % T::SLOTS) * T::PLANE;
+        const float* Pm1 = ring + ((z - 1) % T::SLOTS) * T::PLANE;
+        const float* Pp1 = ring + ((z + 1) % T::SLOTS) * T::PLANE;
+        const float* Pm2 = ring + ((z - 2) % T::SLOTS) * T::PLANE;
+        const float* Pp2 = ring + ((z + 2) % T::SLOTS) * T::PLANE;
+
+#pragma unroll 1
+        for (int half = 0; half < T::RPT; ++half) {
+            const int yl = ty + (T::TY / T::RPT) * half;
+            const int y = by * T::TY + yl;
+            // ---- phase A: second differences, the diagonal-sum test, append survivors ----
+            bool surv[4] = { false, false, false, false };
+            float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
+            if (y >= 2 && y <= h - 3 && any_x) {
+                quad_hessians(P0, Pm1, Pp1, Pm2, Pp2, (yl + 2) * T::PW + 4 * tx, qs, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const float2 sxy = vadd(Hxx[g], Hyy[g]), sxz = vadd(Hxx[g], Hzz[g]), syz = vadd(Hyy[g], Hzz[g]);
+                    surv[2 * g] = m[2 * g] && fmaxf(fmaxf(sxy.x, sxz.x), syz.x) <= 0.0f;
+                    surv[2 * g + 1] = m[2 * g + 1] && fmaxf(fmaxf(sxy.y, sxz.y), syz.y) <= 0.0f;
+                }
+            }
+            const unsigned b0 = __ballot_sync(0xffffffffu, surv[0]), b1 = __ballot_sync(0xffffffffu, surv[1]);
+            const unsigned b2 = __ballot_sync(0xffffffffu, surv[2]), b3 = __ballot_sync(0xffffffffu, surv[3]);
+            const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+            int base = 0;
+            if (tx == 0 && n0 + n1 + n2 + n3 > 0) base = atomicAdd(&s_count, n0 + n1 + n2 + n3);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned below = (1u << tx) - 1u;
+            const int slot[4] = { base + __popc(b0 & below), base + n0 + __popc(b1 & below),
+                                  base + n0 + n1 + __popc(b2 & below), base + n0 + n1 + n2 + __popc(b3 & below) };
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (surv[j]) {
+                    typedef Lanes<float2> L2;
+                    const int e = slot[j];
+                    q_h[e] = L2::get(Hxx[j >> 1], j & 1);
+                    q_h[Q::CAP + e] = L2::get(Hxy[j >> 1], j & 1);
+                    q_h[2 * Q::CAP + e] = L2::get(Hxz[j >> 1], j & 1);
+                    q_h[3 * Q::CAP + e] = L2::get(Hyy[j >> 1], j & 1);
+                    q_h[4 * Q::CAP + e] = L2::get(Hyz[j >> 1], j & 1);
+                    q_h[5 * Q::CAP + e] = L2::get(Hzz[j >> 1], j & 1);
+                    q_pos[e] = ((z - zs) << 11) | (yl << 7) | (4 * tx + j);
+                }
+            __syncthreads();                      // appended entries and the count are visible
+            // ---- phase B: full batches off the top of the queue (everything on the very last pass) ----
+            int n = s_count;
+            const bool flush = z + 1 == ze && half + 1 == T::RPT;
+            while (n >= Q::BATCH || (flush && n > 0)) {
+                const int take = min(n, Q::BATCH);
+                drain(n - take, take);
+                n -= take;
+            }
+            __syncthreads();                      // every read of the drained entries is done
+            if (tid == 0) s_count = n;
+            if (half + 1 < T::RPT) __syncthreads();   // (the next plane's barrier covers the last half)
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
+    if (tx == 0 && vmax > 0.0f) atomicMax(p.minmax + 1, __float_as_int(vmax));
 }
 
 // K3b: the shell.  Thread index -> region: z faces (whole planes), then y faces
@@ -765,7 +953,7 @@ hessian_eigen_shell_kernel(const __grid_constant__ VoxelParams p)
         for (int s = 16; s > 0; s >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
         if ((threadIdx.x & 31) == 0 && mn < 3.0e38f) atomicMin(p.minmax + 0, __float_as_int(mn));
     }
-    if (p.last_scale) {
+    {
         float mx = active ? jv : 0.0f;
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
