@@ -478,10 +478,13 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
     if (D) return launch_voxel_t<2>(p, nblocks, nshell, s.s_main);
     if (si == 0) return launch_voxel_t<0>(p, nblocks, nshell, s.s_main);
     if (H->blackwhite) return launch_voxel_t<1>(p, nblocks, nshell, s.s_main);
-    if (p.zchunk >= (1 << 20)) return launch_voxel_t<1, true>(p, nblocks, nshell, s.s_main);   // packed z offset has 20 bits
-    // later scale of a bright-ridge run: the compacting kernel, then the shell
+    if (p.zchunk >= (1 << 21)) return launch_voxel_t<1, true>(p, nblocks, nshell, s.s_main);   // packed z offset has 21 bits
+    // later scale of a bright-ridge run: the compacting kernel (its own 128 x 8 tiling), then the shell
     if (nblocks > 0) {
-        constexpr int smem = HessTile::SMEM_BYTES + HessQueue::BYTES;
+        p.nty = (H->h + HessTileC::TY - 1) / HessTileC::TY;
+        nblocks = (long long)p.ntx * p.nty * nzc;
+        if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+        constexpr int smem = HessTileC::SMEM_BYTES + HessQueue::BYTES;
         static thread_local int configured_dev[64] = { 0 };
         int dev = 0;
         CK(cudaGetDevice(&dev));
@@ -489,7 +492,7 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
             CK(cudaFuncSetAttribute(hessian_eigen_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured_dev[dev] = 1;
         }
-        hessian_eigen_compact_kernel<<<(unsigned)nblocks, HessTile::NT, smem, s.s_main>>>(p);
+        hessian_eigen_compact_kernel<<<(unsigned)nblocks, HessTileC::NT, smem, s.s_main>>>(p);
         g_launches++;
         CK(cudaGetLastError());
     }

@@ -740,22 +740,33 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
 // thread takes two entries through the packed eigen stage and updates J / V where the response
 // beats the stored one, so the expensive stage always runs with full lanes.  The queue persists
 // across planes and is flushed at the end of the chunk.
+struct HessTileC {                               // tile of the compacting kernel: 128 x 8, one row per warp
+    static constexpr int TX = 128, TY = 8, NT = 256;
+    static constexpr int PW = HessTile::PW;      // same row pitch as HessTile (quad_hessians relies on it)
+    static constexpr int PH = TY + 4;
+    static constexpr int PLANE = PW * PH;        // 1584 floats
+    static constexpr int SLOTS = 6;
+    static constexpr int SMEM_BYTES = SLOTS * PLANE * 4;   // 38016
+};
 struct HessQueue {
-    static constexpr int BATCH = 2 * HessTile::NT;                                   // 512 entries
-    static constexpr int HALF = HessTile::TX * HessTile::TY / HessTile::RPT;           // appended between drains
-    static constexpr int CAP = BATCH + HALF;                                           // leftover < BATCH, plus one half plane
-    static constexpr int BYTES = CAP * 7 * 4;
+    static constexpr int BATCH = 2 * HessTileC::NT;                  // 512 entries per drain
+    static constexpr int APPEND = HessTileC::TX * HessTileC::TY;     // most one plane can add (1024)
+    // Appends only happen right after the plane barrier, when at most BATCH - 1 entries are pending
+    // and no drain is in flight, so BATCH + APPEND ring entries can never collide.
+    static constexpr int CAP = BATCH + APPEND;
+    static constexpr int FIELDS = 8;                                 // 6 second differences, J, position
+    static constexpr int BYTES = CAP * FIELDS * 4;                   // 49152
 };
 
-__global__ void __launch_bounds__(HessTile::NT, 2)
+__global__ void __launch_bounds__(HessTileC::NT, 2)
 hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
 {
-    using T = HessTile;
+    using T = HessTileC;
     using Q = HessQueue;
     extern __shared__ __align__(16) float ring[];
-    float* q_h = ring + T::SLOTS * T::PLANE;               // 6 arrays of CAP floats
-    int* q_pos = reinterpret_cast<int*>(q_h + 6 * Q::CAP);
-    __shared__ int s_count;
+    float* q_h = ring + T::SLOTS * T::PLANE;               // 7 arrays of CAP floats: Dxx Dxy Dxz Dyy Dyz Dzz Jold
+    int* q_pos = reinterpret_cast<int*>(q_h + 7 * Q::CAP);
+    __shared__ unsigned s_tail;                            // entries ever appended (the ring index is tail % CAP)
     const int tid = threadIdx.x;
     const int tx = tid & 31, ty = tid >> 5;
     int bid = blockIdx.x;
@@ -767,7 +778,7 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     const int zs = max(p.z_begin + bz * p.zchunk, 2);
     const int ze = min(min(p.z_begin + (bz + 1) * p.zchunk, p.z_begin + p.nz), l - 2);
     if (zs >= ze) return;
-    if (tid == 0) s_count = 0;
+    if (tid == 0) s_tail = 0;
 
     constexpr int UNITS = T::PLANE / 2, UPR = T::PW / 2;
     constexpr int NU = (UNITS + T::NT - 1) / T::NT;
@@ -802,15 +813,17 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
 #pragma unroll
     for (int j = 0; j < 4; ++j) m[j] = xq + j >= 2 && xq + j <= w - 3;
     const bool any_x = m[0] || m[1] || m[2] || m[3];
+    const bool vec_j = p.vec_ok && xq + 3 < w;
     const float qs = 0.25f * p.k.sigma2;
     float vmax = 0.0f;
+    unsigned head = 0;        // entries [head, tail) are pending; every thread carries the same value
 
-    // Phase B on entries [first, first + count): two per thread
-    auto drain = [&](int first, int count) {
-        const int e0 = first + 2 * tid;
+    // Phase B on entries [first, first + count) (ring positions), two per thread
+    auto drain = [&](unsigned first, int count) {
         if (2 * tid >= count) return;
         const bool two = 2 * tid + 1 < count;
-        const int e1 = two ? e0 + 1 : e0;
+        const int e0 = (int)((first + 2 * tid) % Q::CAP);
+        const int e1 = two ? (int)((first + 2 * tid + 1) % Q::CAP) : e0;
         Eig3x2 e;
         eig_sym3<float2, true>(make_float2(q_h[e0], q_h[e1]), make_float2(q_h[Q::CAP + e0], q_h[Q::CAP + e1]),
                                make_float2(q_h[2 * Q::CAP + e0], q_h[2 * Q::CAP + e1]),
@@ -821,11 +834,12 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             if (k == 1 && !two) break;
-            const int pos = q_pos[k ? e1 : e0];              // (z - zs) << 11 | row << 7 | column
-            const int x = bx * T::TX + (pos & 127), y = by * T::TY + ((pos >> 7) & 15), z = zs + (pos >> 11);
-            const long long i = ((long long)(z - p.z_begin) * h + y) * w + x;
+            const int ek = k ? e1 : e0;
             const float vk = k ? v.y : v.x;
-            if (vk > p.J[i]) {
+            if (vk > q_h[6 * Q::CAP + ek]) {
+                const int pos = q_pos[ek];                    // (z - zs) << 10 | row << 7 | column
+                const int x = bx * T::TX + (pos & 127), y = by * T::TY + ((pos >> 7) & 7), z = zs + (pos >> 10);
+                const long long i = ((long long)(z - p.z_begin) * h + y) * w + x;
                 p.J[i] = vk;
                 p.Vx[i] = (uint8_t)dir_code(k ? e.vx.y : e.vx.x);
                 p.Vy[i] = (uint8_t)dir_code(k ? e.vy.y : e.vy.x);
@@ -843,64 +857,66 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
 
     for (int z = zs; z < ze; ++z) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                          // plane z+2 visible; plane z-3's slot and the queue count are settled
+        __syncthreads();                          // plane z+2 visible; nobody reads plane z-3's slot or drains any more
         if (z + 1 < ze) fetch(z + 3);
         const float* P0 = ring + (z % T::SLOTS) * T::PLANE;
         const float* Pm1 = ring + ((z - 1) % T::SLOTS) * T::PLANE;
         const float* Pp1 = ring + ((z + 1) % T::SLOTS) * T::PLANE;
         const float* Pm2 = ring + ((z - 2) % T::SLOTS) * T::PLANE;
         const float* Pp2 = ring + ((z + 2) % T::SLOTS) * T::PLANE;
-
-#pragma unroll 1
-        for (int half = 0; half < T::RPT; ++half) {
-            const int yl = ty + (T::TY / T::RPT) * half;
-            const int y = by * T::TY + yl;
-            // ---- phase A: second differences, the diagonal-sum test, append survivors ----
-            bool surv[4] = { false, false, false, false };
-            float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
-            if (y >= 2 && y <= h - 3 && any_x) {
-                quad_hessians(P0, Pm1, Pp1, Pm2, Pp2, (yl + 2) * T::PW + 4 * tx, qs, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+        const int yl = ty;                        // one tile row per warp
+        const int y = by * T::TY + yl;
+        // ---- phase A: second differences, the diagonal-sum test, append survivors ----
+        bool surv[4] = { false, false, false, false };
+        float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
+        float jold[4] = { 0.f, 0.f, 0.f, 0.f };
+        const long long i0 = ((long long)(z - p.z_begin) * h + y) * w + xq;
+        if (y >= 2 && y <= h - 3 && any_x) {
+            quad_hessians(P0, Pm1, Pp1, Pm2, Pp2, (yl + 2) * T::PW + 4 * tx, qs, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const float2 sxy = vadd(Hxx[g], Hyy[g]), sxz = vadd(Hxx[g], Hzz[g]), syz = vadd(Hyy[g], Hzz[g]);
-                    surv[2 * g] = m[2 * g] && fmaxf(fmaxf(sxy.x, sxz.x), syz.x) <= 0.0f;
-                    surv[2 * g + 1] = m[2 * g + 1] && fmaxf(fmaxf(sxy.y, sxz.y), syz.y) <= 0.0f;
-                }
+            for (int g = 0; g < 2; ++g) {
+                const float2 sxy = vadd(Hxx[g], Hyy[g]), sxz = vadd(Hxx[g], Hzz[g]), syz = vadd(Hyy[g], Hzz[g]);
+                surv[2 * g] = m[2 * g] && fmaxf(fmaxf(sxy.x, sxz.x), syz.x) <= 0.0f;
+                surv[2 * g + 1] = m[2 * g + 1] && fmaxf(fmaxf(sxy.y, sxz.y), syz.y) <= 0.0f;
             }
-            const unsigned b0 = __ballot_sync(0xffffffffu, surv[0]), b1 = __ballot_sync(0xffffffffu, surv[1]);
-            const unsigned b2 = __ballot_sync(0xffffffffu, surv[2]), b3 = __ballot_sync(0xffffffffu, surv[3]);
-            const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-            int base = 0;
-            if (tx == 0 && n0 + n1 + n2 + n3 > 0) base = atomicAdd(&s_count, n0 + n1 + n2 + n3);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const unsigned below = (1u << tx) - 1u;
-            const int slot[4] = { base + __popc(b0 & below), base + n0 + __popc(b1 & below),
-                                  base + n0 + n1 + __popc(b2 & below), base + n0 + n1 + n2 + __popc(b3 & below) };
+            if (surv[0] || surv[1] || surv[2] || surv[3]) {
+                if (vec_j) *reinterpret_cast<float4*>(jold) = *reinterpret_cast<const float4*>(p.J + i0);
+                else
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (surv[j]) {
-                    typedef Lanes<float2> L2;
-                    const int e = slot[j];
-                    q_h[e] = L2::get(Hxx[j >> 1], j & 1);
-                    q_h[Q::CAP + e] = L2::get(Hxy[j >> 1], j & 1);
-                    q_h[2 * Q::CAP + e] = L2::get(Hxz[j >> 1], j & 1);
-                    q_h[3 * Q::CAP + e] = L2::get(Hyy[j >> 1], j & 1);
-                    q_h[4 * Q::CAP + e] = L2::get(Hyz[j >> 1], j & 1);
-                    q_h[5 * Q::CAP + e] = L2::get(Hzz[j >> 1], j & 1);
-                    q_pos[e] = ((z - zs) << 11) | (yl << 7) | (4 * tx + j);
-                }
-            __syncthreads();                      // appended entries and the count are visible
-            // ---- phase B: full batches off the top of the queue (everything on the very last pass) ----
-            int n = s_count;
-            const bool flush = z + 1 == ze && half + 1 == T::RPT;
-            while (n >= Q::BATCH || (flush && n > 0)) {
-                const int take = min(n, Q::BATCH);
-                drain(n - take, take);
-                n -= take;
+                    for (int j = 0; j < 4; ++j) if (surv[j]) jold[j] = p.J[i0 + j];
             }
-            __syncthreads();                      // every read of the drained entries is done
-            if (tid == 0) s_count = n;
-            if (half + 1 < T::RPT) __syncthreads();   // (the next plane's barrier covers the last half)
+        }
+        const unsigned b0 = __ballot_sync(0xffffffffu, surv[0]), b1 = __ballot_sync(0xffffffffu, surv[1]);
+        const unsigned b2 = __ballot_sync(0xffffffffu, surv[2]), b3 = __ballot_sync(0xffffffffu, surv[3]);
+        const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+        unsigned base = 0;
+        if (tx == 0 && n0 + n1 + n2 + n3 > 0) base = atomicAdd(&s_tail, (unsigned)(n0 + n1 + n2 + n3));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned below = (1u << tx) - 1u;
+        const unsigned slot[4] = { base + __popc(b0 & below), base + n0 + __popc(b1 & below),
+                                   base + n0 + n1 + __popc(b2 & below), base + n0 + n1 + n2 + __popc(b3 & below) };
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (surv[j]) {
+                typedef Lanes<float2> L2;
+                const int e = (int)(slot[j] % Q::CAP);
+                q_h[e] = L2::get(Hxx[j >> 1], j & 1);
+                q_h[Q::CAP + e] = L2::get(Hxy[j >> 1], j & 1);
+                q_h[2 * Q::CAP + e] = L2::get(Hxz[j >> 1], j & 1);
+                q_h[3 * Q::CAP + e] = L2::get(Hyy[j >> 1], j & 1);
+                q_h[4 * Q::CAP + e] = L2::get(Hyz[j >> 1], j & 1);
+                q_h[5 * Q::CAP + e] = L2::get(Hzz[j >> 1], j & 1);
+                q_h[6 * Q::CAP + e] = jold[j];
+                q_pos[e] = ((z - zs) << 10) | (yl << 7) | (4 * tx + j);
+            }
+        __syncthreads();                          // appended entries and the tail are visible
+        // ---- phase B: full batches from the head of the queue (everything after the last plane) ----
+        const unsigned tail = s_tail;
+        const bool flush = z + 1 == ze;
+        while (tail - head >= (unsigned)Q::BATCH || (flush && tail != head)) {
+            const int take = (int)min(tail - head, (unsigned)Q::BATCH);
+            drain(head, take);
+            head += take;
         }
     }
 #pragma unroll
