@@ -749,13 +749,15 @@ struct HessTileC {                               // tile of the compacting kerne
     static constexpr int SMEM_BYTES = SLOTS * PLANE * 4;   // 38016
 };
 struct HessQueue {
-    static constexpr int BATCH = 2 * HessTileC::NT;                  // 512 entries per drain
+    static constexpr int PAIRS = 2;                                  // packed pairs per thread per drain (ILP)
+    static constexpr int BATCH = 2 * PAIRS * HessTileC::NT;          // 1024 entries per drain
     static constexpr int APPEND = HessTileC::TX * HessTileC::TY;     // most one plane can add (1024)
     // Appends only happen right after the plane barrier, when at most BATCH - 1 entries are pending
-    // and no drain is in flight, so BATCH + APPEND ring entries can never collide.
-    static constexpr int CAP = BATCH + APPEND;
-    static constexpr int FIELDS = 8;                                 // 6 second differences, J, position
-    static constexpr int BYTES = CAP * FIELDS * 4;                   // 49152
+    // and no drain is in flight, so BATCH + APPEND ring entries can never collide; rounded up to a
+    // power of two so that the ring index is a mask.
+    static constexpr int CAP = 2048;
+    static_assert(CAP >= BATCH + APPEND, "queue too small");
+    static constexpr int BYTES = CAP * 32;                           // entry = 2 x float4: {Dxx,Dxy,Dxz,Dyy} {Dyz,Dzz,J,pos}
 };
 
 __global__ void __launch_bounds__(HessTileC::NT, 2)
@@ -764,8 +766,7 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     using T = HessTileC;
     using Q = HessQueue;
     extern __shared__ __align__(16) float ring[];
-    float* q_h = ring + T::SLOTS * T::PLANE;               // 7 arrays of CAP floats: Dxx Dxy Dxz Dyy Dyz Dzz Jold
-    int* q_pos = reinterpret_cast<int*>(q_h + 7 * Q::CAP);
+    float4* q4 = reinterpret_cast<float4*>(ring + T::SLOTS * T::PLANE);   // CAP entries of 2 float4
     __shared__ unsigned s_tail;                            // entries ever appended (the ring index is tail % CAP)
     const int tid = threadIdx.x;
     const int tx = tid & 31, ty = tid >> 5;
@@ -817,40 +818,54 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     const float qs = 0.25f * p.k.sigma2;
     float vmax = 0.0f;
     unsigned head = 0;        // entries [head, tail) are pending; every thread carries the same value
-
-    // Phase B on entries [first, first + count) (ring positions), two per thread
-    auto drain = [&](unsigned first, int count) {
-        if (2 * tid >= count) return;
-        const bool two = 2 * tid + 1 < count;
-        const int e0 = (int)((first + 2 * tid) % Q::CAP);
-        const int e1 = two ? (int)((first + 2 * tid + 1) % Q::CAP) : e0;
-        Eig3x2 e;
-        eig_sym3<float2, true>(make_float2(q_h[e0], q_h[e1]), make_float2(q_h[Q::CAP + e0], q_h[Q::CAP + e1]),
-                               make_float2(q_h[2 * Q::CAP + e0], q_h[2 * Q::CAP + e1]),
-                               make_float2(q_h[3 * Q::CAP + e0], q_h[3 * Q::CAP + e1]),
-                               make_float2(q_h[4 * Q::CAP + e0], q_h[4 * Q::CAP + e1]),
-                               make_float2(q_h[5 * Q::CAP + e0], q_h[5 * Q::CAP + e1]), e);
-        const float2 v = vesselness<float2, true>(e, p.k);
+    // The stored response of the thread's quad is fetched one plane ahead, so that the load is in
+    // flight during a whole plane of work instead of stalling the append.
+    const int yrow = by * T::TY + ty;
+    const bool row_ok = yrow >= 2 && yrow <= h - 3 && any_x;
+    float jnext[4] = { 0.f, 0.f, 0.f, 0.f };
+    auto load_j = [&](int z) {
+        const long long i0 = ((long long)(z - p.z_begin) * h + yrow) * w + xq;
+        if (vec_j) *reinterpret_cast<float4*>(jnext) = __ldcs(reinterpret_cast<const float4*>(p.J + i0));
+        else
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            if (k == 1 && !two) break;
-            const int ek = k ? e1 : e0;
-            const float vk = k ? v.y : v.x;
-            if (vk > q_h[6 * Q::CAP + ek]) {
-                const int pos = q_pos[ek];                    // (z - zs) << 10 | row << 7 | column
-                const int x = bx * T::TX + (pos & 127), y = by * T::TY + ((pos >> 7) & 7), z = zs + (pos >> 10);
-                const long long i = ((long long)(z - p.z_begin) * h + y) * w + x;
-                p.J[i] = vk;
-                p.Vx[i] = (uint8_t)dir_code(k ? e.vx.y : e.vx.x);
-                p.Vy[i] = (uint8_t)dir_code(k ? e.vy.y : e.vy.x);
-                p.Vz[i] = (uint8_t)dir_code(k ? e.vz.y : e.vz.x);
-                if (p.scale_idx) p.scale_idx[i] = (uint8_t)p.scale;
-                if (p.dir) {
-                    p.dir[i] = k ? e.vx.y : e.vx.x;
-                    p.dir[p.voxels + i] = k ? e.vy.y : e.vy.x;
-                    p.dir[2 * p.voxels + i] = k ? e.vz.y : e.vz.x;
+            for (int j = 0; j < 4; ++j) if (m[j]) jnext[j] = p.J[i0 + j];
+    };
+    if (row_ok) load_j(zs);
+
+    // Phase B on entries [first, first + count) (ring positions): PAIRS independent packed pairs per thread
+    auto drain = [&](unsigned first, int count) {
+#pragma unroll
+        for (int q = 0; q < Q::PAIRS; ++q) {
+            const int o = 2 * (tid + q * T::NT);           // entries o, o + 1 of the batch
+            if (o >= count) continue;
+            const bool two = o + 1 < count;
+            const int e0 = (int)((first + o) & (Q::CAP - 1));
+            const int e1 = two ? (int)((first + o + 1) & (Q::CAP - 1)) : e0;
+            const float4 a0 = q4[2 * e0], c0 = q4[2 * e0 + 1], a1 = q4[2 * e1], c1 = q4[2 * e1 + 1];
+            Eig3x2 e;
+            eig_sym3<float2, true>(make_float2(a0.x, a1.x), make_float2(a0.y, a1.y), make_float2(a0.z, a1.z),
+                                   make_float2(a0.w, a1.w), make_float2(c0.x, c1.x), make_float2(c0.y, c1.y), e);
+            const float2 v = vesselness<float2, true>(e, p.k);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k == 1 && !two) break;
+                const float vk = k ? v.y : v.x;
+                if (vk > (k ? c1.z : c0.z)) {
+                    const int pos = __float_as_int(k ? c1.w : c0.w);   // (z - zs) << 10 | row << 7 | column
+                    const int x = bx * T::TX + (pos & 127), y = by * T::TY + ((pos >> 7) & 7), z = zs + (pos >> 10);
+                    const long long i = ((long long)(z - p.z_begin) * h + y) * w + x;
+                    p.J[i] = vk;
+                    p.Vx[i] = (uint8_t)dir_code(k ? e.vx.y : e.vx.x);
+                    p.Vy[i] = (uint8_t)dir_code(k ? e.vy.y : e.vy.x);
+                    p.Vz[i] = (uint8_t)dir_code(k ? e.vz.y : e.vz.x);
+                    if (p.scale_idx) p.scale_idx[i] = (uint8_t)p.scale;
+                    if (p.dir) {
+                        p.dir[i] = k ? e.vx.y : e.vx.x;
+                        p.dir[p.voxels + i] = k ? e.vy.y : e.vy.x;
+                        p.dir[2 * p.voxels + i] = k ? e.vz.y : e.vz.x;
+                    }
+                    vmax = fmaxf(vmax, vk);
                 }
-                vmax = fmaxf(vmax, vk);
             }
         }
     };
@@ -869,21 +884,15 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         // ---- phase A: second differences, the diagonal-sum test, append survivors ----
         bool surv[4] = { false, false, false, false };
         float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
-        float jold[4] = { 0.f, 0.f, 0.f, 0.f };
-        const long long i0 = ((long long)(z - p.z_begin) * h + y) * w + xq;
-        if (y >= 2 && y <= h - 3 && any_x) {
+        const float jold[4] = { jnext[0], jnext[1], jnext[2], jnext[3] };
+        if (row_ok && z + 1 < ze) load_j(z + 1);
+        if (row_ok) {
             quad_hessians(P0, Pm1, Pp1, Pm2, Pp2, (yl + 2) * T::PW + 4 * tx, qs, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 const float2 sxy = vadd(Hxx[g], Hyy[g]), sxz = vadd(Hxx[g], Hzz[g]), syz = vadd(Hyy[g], Hzz[g]);
                 surv[2 * g] = m[2 * g] && fmaxf(fmaxf(sxy.x, sxz.x), syz.x) <= 0.0f;
                 surv[2 * g + 1] = m[2 * g + 1] && fmaxf(fmaxf(sxy.y, sxz.y), syz.y) <= 0.0f;
-            }
-            if (surv[0] || surv[1] || surv[2] || surv[3]) {
-                if (vec_j) *reinterpret_cast<float4*>(jold) = *reinterpret_cast<const float4*>(p.J + i0);
-                else
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (surv[j]) jold[j] = p.J[i0 + j];
             }
         }
         const unsigned b0 = __ballot_sync(0xffffffffu, surv[0]), b1 = __ballot_sync(0xffffffffu, surv[1]);
@@ -899,15 +908,11 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         for (int j = 0; j < 4; ++j)
             if (surv[j]) {
                 typedef Lanes<float2> L2;
-                const int e = (int)(slot[j] % Q::CAP);
-                q_h[e] = L2::get(Hxx[j >> 1], j & 1);
-                q_h[Q::CAP + e] = L2::get(Hxy[j >> 1], j & 1);
-                q_h[2 * Q::CAP + e] = L2::get(Hxz[j >> 1], j & 1);
-                q_h[3 * Q::CAP + e] = L2::get(Hyy[j >> 1], j & 1);
-                q_h[4 * Q::CAP + e] = L2::get(Hyz[j >> 1], j & 1);
-                q_h[5 * Q::CAP + e] = L2::get(Hzz[j >> 1], j & 1);
-                q_h[6 * Q::CAP + e] = jold[j];
-                q_pos[e] = ((z - zs) << 10) | (yl << 7) | (4 * tx + j);
+                const int e = (int)(slot[j] & (Q::CAP - 1));
+                q4[2 * e] = make_float4(L2::get(Hxx[j >> 1], j & 1), L2::get(Hxy[j >> 1], j & 1),
+                                        L2::get(Hxz[j >> 1], j & 1), L2::get(Hyy[j >> 1], j & 1));
+                q4[2 * e + 1] = make_float4(L2::get(Hyz[j >> 1], j & 1), L2::get(Hzz[j >> 1], j & 1), jold[j],
+                                            __int_as_float(((z - zs) << 10) | (yl << 7) | (4 * tx + j)));
             }
         __syncthreads();                          // appended entries and the tail are visible
         // ---- phase B: full batches from the head of the queue (everything after the last plane) ----
