@@ -91,6 +91,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--verify", action="store_true",
+                    help="N > 1: check every rank's slab of J / V bit for bit against a one-GPU run of the whole volume on rank 0")
     return ap.parse_args()
 
 
@@ -342,6 +344,35 @@ def run_ours(a, sigmas, w, h, l):
     ms_per_step = ms_total / a.steps
     value = total_vox / (ms_per_step * 1e-3)
 
+    # ---- optional: N-slab result == 1-GPU result, bit for bit --------------------------
+    verify = None
+    if a.verify:
+        import zlib
+        out = plan.download()
+        crc = [zlib.crc32(out[k].tobytes()) for k in ("J", "Vx", "Vy", "Vz")]
+        mine = torch.tensor(crc + [z0, z1], dtype=torch.int64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, mine)
+        else:
+            allr = [mine]
+        if rank == 0:
+            whole = FrangiPlan(sigmas, ZDIST, ALPHA, BETA, CC, False, w, h, l, flags=flags, devices=(local_rank,))
+            hw = workload_slab(w, h, l, 0, l)
+            whole.upload(hw)
+            wj = whole.run_resident()
+            ref = whole.download()
+            whole.close()
+            bad = []
+            for r_, t_ in enumerate(allr):
+                t_ = [int(x) for x in t_.cpu()]
+                a0, a1 = t_[4], t_[5]
+                want = [zlib.crc32(ref[k][a0:a1].tobytes()) for k in ("J", "Vx", "Vy", "Vz")]
+                if want != t_[:4]:
+                    bad.append(r_)
+            verify = {"slabs": world, "mismatching_ranks": bad, "jmax_whole": wj[1], "jmax_slabs": jmax}
+        del out
+
     # ---- end to end through the C-ABI call with host buffers ----------------------
     e2e = None
     if not a.no_e2e:
@@ -435,6 +466,8 @@ def run_ours(a, sigmas, w, h, l):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "jmin": jmin, "jmax": jmax,
     }
+    if verify is not None:
+        line["verify"] = verify
     print(json.dumps(line), flush=True)
     plan.close()
     if world > 1:
