@@ -1036,15 +1036,30 @@ vesselness_stage_scalar_kernel(const float* __restrict__ Dxx, const float* __res
 // K4: J -> J8 (Advantra_plugin.cpp:2499-2512, round() from :120-123).
 // minmax holds the float bit patterns of Jmin / Jmax (after the all-reduce).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t j8_code(float j, float lo, float range, bool flat)
+// One voxel of K4.  The reference computes round(((J-Jmin)/(Jmax-Jmin))*255) with an IEEE float
+// division, a float multiply and round-half-away (Advantra_plugin.cpp:120-123, 2508).
+//  * division by the loop-invariant range: q0 = a*y, r = fma(-q0, b, a), q = fma(r, y, q0) with
+//    y = RN(1/b) is the correctly rounded quotient (Markstein) unless b's significand is all ones
+//    or the operands leave the comfortable exponent range; `fast` is false in those cases and the
+//    plain division is used;
+//  * rounding without conversions: t = qf + 2^23 rounds to nearest-even in the adder, the exact
+//    difference tells a tie that went down, and the byte sits in the low mantissa bits of t.
+__device__ __forceinline__ uint32_t j8_code(float j, float lo, float range, float y, bool fast, bool flat)
 {
-    if (flat) return 0;
-    const float qf = __fmul_rn(__fdiv_rn(__fsub_rn(j, lo), range), 255.0f);
-    // round half away from zero (Advantra_plugin.cpp:120-123), exactly: trunc, then the exact
-    // fractional part decides (qf + 0.5f could round up across .5); negatives clamp to 0 anyway
-    int v = (int)qf;
-    v += (__fsub_rn(qf, (float)v) >= 0.5f) ? 1 : 0;
-    return (uint8_t)min(max(v, 0), 255);
+    const float a = __fsub_rn(j, lo);
+    float q;
+    if (fast) {
+        const float q0 = __fmul_rn(a, y);
+        const float r = __fmaf_rn(-q0, range, a);
+        q = __fmaf_rn(r, y, q0);
+    } else {
+        q = __fdiv_rn(a, range);
+    }
+    const float qf = fminf(fmaxf(__fmul_rn(q, 255.0f), 0.0f), 255.0f);   // the reference clamps after rounding: same bytes
+    const float t = __fadd_rn(qf, 8388608.0f);
+    const float rn = __fsub_rn(t, 8388608.0f);
+    const uint32_t v = (__float_as_uint(t) & 0x1ffu) + (__fsub_rn(qf, rn) == 0.5f ? 1u : 0u);
+    return flat ? 0u : v;
 }
 
 __global__ void __launch_bounds__(256)
@@ -1054,6 +1069,10 @@ j_to_j8_kernel(const float* __restrict__ J, uint8_t* __restrict__ J8, long long 
     const float hi = __int_as_float(minmax[1]);
     const float range = __fsub_rn(hi, lo);
     const bool flat = fabsf(range) <= 1.175494351e-38f;  // FLT_MIN
+    const float y = __frcp_rn(range);
+    const uint32_t rb = __float_as_uint(range);
+    const int ex = (int)((rb >> 23) & 0xffu);
+    const bool fast = (rb & 0x7fffffu) != 0x7fffffu && ex > 64 && ex < 190 && fabsf(lo) < 1e18f && fabsf(hi) < 1e18f;
     const long long n16 = n / 16;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n16; g += stride) {
@@ -1064,12 +1083,12 @@ j_to_j8_kernel(const float* __restrict__ J, uint8_t* __restrict__ J8, long long 
         uint32_t o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            o[k] = (uint32_t)j8_code(q[k].x, lo, range, flat) | ((uint32_t)j8_code(q[k].y, lo, range, flat) << 8) |
-                   ((uint32_t)j8_code(q[k].z, lo, range, flat) << 16) | ((uint32_t)j8_code(q[k].w, lo, range, flat) << 24);
-        reinterpret_cast<uint4*>(J8)[g] = make_uint4(o[0], o[1], o[2], o[3]);
+            o[k] = j8_code(q[k].x, lo, range, y, fast, flat) | (j8_code(q[k].y, lo, range, y, fast, flat) << 8) |
+                   (j8_code(q[k].z, lo, range, y, fast, flat) << 16) | (j8_code(q[k].w, lo, range, y, fast, flat) << 24);
+        __stcs(reinterpret_cast<uint4*>(J8) + g, make_uint4(o[0], o[1], o[2], o[3]));
     }
     for (long long i = 16 * n16 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        J8[i] = j8_code(J[i], lo, range, flat);
+        J8[i] = (uint8_t)j8_code(J[i], lo, range, y, fast, flat);
 }
 
 // min / max over the per-slab pairs gathered on one device (local-copy multi-slab mode)
