@@ -121,6 +121,39 @@ int launch_xy_t(const XYParams& p, const GaussTaps& t, int nblocks, cudaStream_t
     return 0;
 }
 
+template <int L>
+int launch_xy_fma_t(const XYParams& p, const GaussTaps& t, int nblocks, cudaStream_t s)
+{
+    using C = XYFmaCfg<L>;
+    auto k = gauss_xy_fma_kernel<L>;
+    static thread_local int configured_dev[64] = { 0 };
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 64 && !configured_dev[dev]) {
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured_dev[dev] = 1;
+    }
+    k<<<nblocks, C::NT, C::SMEM_BYTES, s>>>(p, t);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int launch_xy_fma(int L, const XYParams& p, const GaussTaps& t, int nblocks, cudaStream_t s)
+{
+    switch (L) {
+        case 3: return launch_xy_fma_t<3>(p, t, nblocks, s);
+        case 6: return launch_xy_fma_t<6>(p, t, nblocks, s);
+        case 9: return launch_xy_fma_t<9>(p, t, nblocks, s);
+        case 12: return launch_xy_fma_t<12>(p, t, nblocks, s);
+        case 15: return launch_xy_fma_t<15>(p, t, nblocks, s);
+        case 18: return launch_xy_fma_t<18>(p, t, nblocks, s);
+        case 24: return launch_xy_fma_t<24>(p, t, nblocks, s);
+        case 30: return launch_xy_fma_t<30>(p, t, nblocks, s);
+    }
+    return fail(FRANGI_GPU_EINVAL, "no gauss_xy instantiation for radius %d", L);
+}
+
 template <bool EXACT>
 int launch_xy_e(int L, const XYParams& p, const GaussTaps& t, int nblocks, cudaStream_t s)
 {
@@ -331,15 +364,19 @@ int launch_xy(frangi_gpu* H, Slab& s, const ScalePlan& sp, const uint8_t* I_own,
     p.vec_ok = (H->w % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.I) & 3) == 0);
     const long long nblocks = (long long)p.nstrips * p.nsegs * p.nz;
     if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+#ifndef XY_FMA_PACKED
+#define XY_FMA_PACKED 1
+#endif
     if (H->flags & FRANGI_GPU_FLAG_FMA_SMOOTHING)
-        return launch_xy_e<false>(sp.rxy_t, p, sp.txy, (int)nblocks, s.s_main);
+        return XY_FMA_PACKED ? launch_xy_fma(sp.rxy_t, p, sp.txy, (int)nblocks, s.s_main)
+                             : launch_xy_e<false>(sp.rxy_t, p, sp.txy, (int)nblocks, s.s_main);
     return launch_xy_e<true>(sp.rxy_t, p, sp.txy, (int)nblocks, s.s_main);
 }
 
 template <int L, bool EXACT>
 int launch_zm_t(const ZParams& p, const GaussTaps& t, long long nblocks, cudaStream_t s)
 {
-    gauss_z_march_kernel<L, EXACT><<<(unsigned)nblocks, 128, 0, s>>>(p, t);
+    gauss_z_march_kernel<L, EXACT><<<(unsigned)nblocks, ZM_THREADS, 0, s>>>(p, t);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
@@ -368,7 +405,7 @@ int launch_z(frangi_gpu* H, Slab& s, const ScalePlan& sp)
     const bool fma = (H->flags & FRANGI_GPU_FLAG_FMA_SMOOTHING) != 0;
     if (sp.rz_t <= 12) {
         // marching form: one chunk per column unless the plane alone cannot fill the GPU
-        p.nxs = (H->w + 255) / 256;
+        p.nxs = (H->w + 2 * ZM_THREADS - 1) / (2 * ZM_THREADS);
         const long long cols = (long long)p.nxs * H->h;
         long long nzc = std::max<long long>(1, std::min<long long>((1184 + cols - 1) / cols, (p.out_count + 15) / 16));
         p.zchunk = (int)((p.out_count + nzc - 1) / nzc);

@@ -225,6 +225,183 @@ gauss_xy_kernel(const __grid_constant__ XYParams p, const __grid_constant__ Gaus
 }
 
 // ---------------------------------------------------------------------------
+// K1, FMA mode: the same strip / batch / ring structure with both passes in packed
+// float32x2 (FFMA2 with the tap as a broadcast scalar operand), which halves the issue
+// slots of the multiply-adds.  The x pass pairs the SAME output column of two adjacent
+// rows, so the staged rows are interleaved in pairs ({row 2p, row 2p+1} per column) and
+// a 128-bit shared load yields two ready register pairs; a thread makes 8 columns x 2
+// rows.  The y pass pairs two adjacent columns of one row (a 64-bit load from the ring
+// is a ready pair); a thread makes 8 rows x 2 columns and stores 64-bit.
+// ---------------------------------------------------------------------------
+template <int L>
+struct XYFmaCfg {
+    static constexpr int TW = 256;
+    static constexpr int RB = 16;
+    static constexpr int NT = 256;
+    static constexpr int LAL = (L + 3) / 4 * 4;
+    static constexpr int PIN0 = TW + 2 * LAL;                       // staged columns per row
+    static constexpr int PINP = ((PIN0 + 13) / 16) * 16 + 2;        // >= PIN0 and = 2 mod 16
+    static constexpr int PP = 2 * PINP;                             // floats per row pair: = 4 mod 32 (conflict-free LDS.128)
+    static constexpr int PR = TW + 4;
+    static constexpr int NBLK = 1 + (2 * L + RB - 1) / RB;
+    static constexpr int SMEM_BYTES = ((RB / 2) * PP + NBLK * RB * PR) * 4;
+};
+
+template <int L, int YH>
+__device__ __forceinline__ void xy_fma_ypass(const float* s_ring, const GaussTaps& taps, int b, int ycp, float* Oz, int x0,
+                                             int ys, int ye, int w, int fpitch)
+{
+    using C = XYFmaCfg<L>;
+    float2 acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = make_float2(0.0f, 0.0f);
+    const float* bp[C::NBLK];
+    int blk = b % C::NBLK;
+#pragma unroll
+    for (int q = 0; q < C::NBLK; ++q) {
+        bp[q] = s_ring + blk * C::RB * C::PR + 2 * ycp;
+        blk = (blk + 1 == C::NBLK) ? 0 : blk + 1;
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8 + 2 * L; ++jj) {
+        constexpr int dummy = 0; (void)dummy;
+        const int rr = jj + 8 * YH;              // ring row of the batch's window
+        const float2 v = *reinterpret_cast<const float2*>(bp[rr / C::RB] + (rr % C::RB) * C::PR);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const int t = jj - o;
+            if (t >= 0 && t <= 2 * L) acc[o] = __ffma2_rn(v, make_float2(taps.g[t], taps.g[t]), acc[o]);
+        }
+    }
+    const int x = x0 + 2 * ycp;
+    const int ybase = ys + b * C::RB + 8 * YH;
+    if (x + 1 < w) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+            if (ybase + o < ye) *reinterpret_cast<float2*>(Oz + (long long)(ybase + o) * fpitch + x) = acc[o];
+    } else if (x < w) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+            if (ybase + o < ye) Oz[(long long)(ybase + o) * fpitch + x] = acc[o].x;
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(256, 2)
+gauss_xy_fma_kernel(const __grid_constant__ XYParams p, const __grid_constant__ GaussTaps taps)
+{
+    using C = XYFmaCfg<L>;
+    extern __shared__ __align__(16) float smem[];
+    float* s_in2 = smem;
+    float* s_ring = smem + (C::RB / 2) * C::PP;
+
+    const int tid = threadIdx.x;
+    const int bid = blockIdx.x;
+    const int strip = bid % p.nstrips;
+    const int seg = (bid / p.nstrips) % p.nsegs;
+    const int z = bid / (p.nstrips * p.nsegs);
+    const int x0 = strip * C::TW;
+    const int ys = seg * p.seg_h;
+    const int ye = min(ys + p.seg_h, p.h);
+    const uint8_t* __restrict__ Iz = p.I + (long long)z * p.w * p.h;
+    float* __restrict__ Oz = p.out + (long long)z * p.fplane;
+
+    const int nb = (ye - ys + C::RB - 1) / C::RB;
+    const int nphases = nb + C::NBLK - 1;
+
+    // staging: a thread fetches the same 4 columns of both rows of a pair (two 32-bit words)
+    constexpr int GROUPS = C::PIN0 / 4;
+    constexpr int NW = ((C::RB / 2) * GROUPS + C::NT - 1) / C::NT;
+    uint32_t raw[NW][2];
+    auto fetch = [&](int ph) {
+        const int r0 = ys - L + ph * C::RB;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            const int idx = tid + k * C::NT;
+            uint32_t u[2] = { 0, 0 };
+            if (idx < (C::RB / 2) * GROUPS) {
+                const int rp = idx / GROUPS;
+                const int g = idx - rp * GROUPS;
+                const int xg = x0 - C::LAL + 4 * g;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int y = clampi(r0 + 2 * rp + q, 0, p.h - 1);
+                    const uint8_t* row = Iz + (long long)y * p.w;
+                    if (p.vec_ok && xg >= 0 && xg + 3 < p.w) {
+                        u[q] = __ldg(reinterpret_cast<const uint32_t*>(row + xg));
+                    } else {
+                        u[q] = (uint32_t)__ldg(row + clampi(xg + 0, 0, p.w - 1)) |
+                               ((uint32_t)__ldg(row + clampi(xg + 1, 0, p.w - 1)) << 8) |
+                               ((uint32_t)__ldg(row + clampi(xg + 2, 0, p.w - 1)) << 16) |
+                               ((uint32_t)__ldg(row + clampi(xg + 3, 0, p.w - 1)) << 24);
+                    }
+                }
+            }
+            raw[k][0] = u[0]; raw[k][1] = u[1];
+        }
+    };
+    fetch(0);
+
+    const int xrp = tid & 7;    // x pass: row pair
+    const int xch = tid >> 3;   // x pass: 8-column chunk
+    const int ycp = tid & 127;  // y pass: column pair
+    const int yh = tid >> 7;    // y pass: upper / lower 8 rows of the batch
+
+    for (int phase = 0; phase < nphases; ++phase) {
+        __syncthreads();  // s_in2 and the ring block about to be overwritten are no longer read
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            const int idx = tid + k * C::NT;
+            if (idx < (C::RB / 2) * GROUPS) {
+                const int rp = idx / GROUPS;
+                const int g = idx - rp * GROUPS;
+                const uint32_t a = raw[k][0], b = raw[k][1];
+                float* dst = s_in2 + rp * C::PP + 8 * g;
+                *reinterpret_cast<float4*>(dst) = make_float4((float)(a & 0xffu), (float)(b & 0xffu),
+                                                              (float)((a >> 8) & 0xffu), (float)((b >> 8) & 0xffu));
+                *reinterpret_cast<float4*>(dst + 4) = make_float4((float)((a >> 16) & 0xffu), (float)((b >> 16) & 0xffu),
+                                                                  (float)(a >> 24), (float)(b >> 24));
+            }
+        }
+        __syncthreads();
+        if (phase + 1 < nphases) fetch(phase + 1);   // in flight during the x and y passes below
+        // ---- x pass: rows 2*xrp, 2*xrp+1, columns 8*xch .. 8*xch+7 ----
+        {
+            float2 acc[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[o] = make_float2(0.0f, 0.0f);
+            const float4* src = reinterpret_cast<const float4*>(s_in2 + xrp * C::PP + 16 * xch);
+#pragma unroll
+            for (int i2 = 0; i2 < (8 + 2 * C::LAL) / 2; ++i2) {
+                const float4 q = src[i2];
+                const float2 e[2] = { make_float2(q.x, q.y), make_float2(q.z, q.w) };
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int i = 2 * i2 + s2;   // window index: column = x0 + 8*xch + i - LAL
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const int t = i - o - C::LAL + L;
+                        if (t >= 0 && t <= 2 * L) acc[o] = __ffma2_rn(e[s2], make_float2(taps.g[t], taps.g[t]), acc[o]);
+                    }
+                }
+            }
+            float* d0 = s_ring + ((phase % C::NBLK) * C::RB + 2 * xrp) * C::PR + 8 * xch;
+            *reinterpret_cast<float4*>(d0) = make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
+            *reinterpret_cast<float4*>(d0 + 4) = make_float4(acc[4].x, acc[5].x, acc[6].x, acc[7].x);
+            *reinterpret_cast<float4*>(d0 + C::PR) = make_float4(acc[0].y, acc[1].y, acc[2].y, acc[3].y);
+            *reinterpret_cast<float4*>(d0 + C::PR + 4) = make_float4(acc[4].y, acc[5].y, acc[6].y, acc[7].y);
+        }
+        const int b = phase - (C::NBLK - 1);     // the batch whose 16 + 2L ring rows are now complete
+        if (b < 0) continue;
+        __syncthreads();
+        // ---- y pass: columns 2*ycp, 2*ycp+1, output rows ys + b*RB + 8*yh + [0, 8) ----
+        // (yh is warp-uniform; the two instantiations keep every ring row index static)
+        if (yh) xy_fma_ypass<L, 1>(s_ring, taps, b, ycp, Oz, x0, ys, ye, p.w, p.fpitch);
+        else xy_fma_ypass<L, 0>(s_ring, taps, b, ycp, Oz, x0, ys, ye, p.w, p.fpitch);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K2: z Gaussian pass.  One thread per (x, y) column and chunk of RZ=8 output
 // planes; the 8+2LZ input planes are read with plane stride (coalesced along
 // x) and replicate-clamped against the GLOBAL volume ends (never at slab
@@ -293,18 +470,27 @@ gauss_z_kernel(const __grid_constant__ ZParams p, const __grid_constant__ GaussT
 // HBM rate.  Accumulation order is the reference's (ascending taps from zero,
 // frangi.cpp:756-768), replicate clamping against the GLOBAL volume ends only.
 // ---------------------------------------------------------------------------
+#ifndef ZM_THREADS
+#define ZM_THREADS 128
+#endif
+#ifndef ZM_PF
+#define ZM_PF 3
+#endif
+#ifndef ZM_MINB
+#define ZM_MINB 1
+#endif
 template <int LZ, bool EXACT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(ZM_THREADS)
 gauss_z_march_kernel(const __grid_constant__ ZParams p, const __grid_constant__ GaussTaps taps)
 {
-    constexpr int PF = 3;
+    constexpr int PF = ZM_PF;
     constexpr int Q = 2 * LZ + 1 + PF;            // ring period
     const long long bid = blockIdx.x;
     const int xs = (int)(bid % p.nxs);
     const long long rest = bid / p.nxs;
     const int y = (int)(rest % p.h);
     const int zc = (int)(rest / p.h);
-    const int x = xs * 256 + 2 * threadIdx.x;
+    const int x = xs * (2 * ZM_THREADS) + 2 * threadIdx.x;
     if (x >= p.w) return;
     const int t_begin = zc * p.zchunk;             // first output plane (relative to out_base) of this chunk
     const int nout = min(p.zchunk, p.out_count - t_begin);
