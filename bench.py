@@ -395,6 +395,20 @@ def run_ours(a, sigmas, w, h, l):
                "steps": k_e2e, "ms_per_step": 1e3 * dt / k_e2e,
                "call": "frangi_gpu_run(I_host -> J_host f32, Jmin, Jmax, Vx, Vy, Vz host u8), pinned host buffers",
                "jmax": float(r["Jmax"])}
+        # the same call as the caller really needs it (J is freed at once, Advantra_plugin.cpp:2514): J8 + V only
+        if world == 1:
+            hJ8 = PinnedBuffer((nz, h, w), np.uint8)
+            plan.run(hI.array, J=None, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array, J8=hJ8.array, want_J=False)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                plan.run(hI.array, J=None, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array, J8=hJ8.array, want_J=False)
+            torch.cuda.synchronize()
+            dt8 = time.perf_counter() - t0
+            e2e["j8_variant"] = {"value": total_vox * k_e2e / dt8, "unit": UNIT, "ms_per_step": 1e3 * dt8 / k_e2e,
+                                 "d2h_bytes_per_step": int(total_vox * 4 + 8),
+                                 "call": "frangi_gpu_run(I_host -> J8, Vx, Vy, Vz host u8; J_host = NULL)"}
+            hJ8.free()
         for b in [hJ] + hV:
             b.free()
 
