@@ -252,7 +252,7 @@ def run_reference_arm(a, sigmas, w, h, l):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -482,14 +482,33 @@ def run_ours(a, sigmas, w, h, l):
     }
     if verify is not None:
         line["verify"] = verify
-    print(json.dumps(line), flush=True)
+    emit(line)
     plan.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def _claim_stdout():
+    """Libraries in this process (NCCL prints its version banner to stdout) must not add lines
+    to the one-JSON-line contract: fd 1 is pointed at stderr and the JSON goes to the saved fd."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     a = parse_args()
     w, h, l = (int(x) for x in a.workload.lower().split("x"))
     sigmas = [float(x) for x in a.sigmas.split(",")]
@@ -498,6 +517,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    _JSON_OUT = _claim_stdout()
     if a.impl == "reference":
         return run_reference_arm(a, sigmas, w, h, l)
     return run_ours(a, sigmas, w, h, l)

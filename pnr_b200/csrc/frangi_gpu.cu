@@ -68,6 +68,7 @@ int fail(int code, const char* fmt, ...)
     } while (0)
 
 // ---- tap planning (host; mirrors frangi.cpp:651-680 in float32) -------------
+constexpr int kEvPerScale = 5;   // timing events recorded per scale (see collect())
 constexpr int kRadii[] = { 3, 6, 9, 12, 15, 18, 24, 30 };
 constexpr int kNumRadii = sizeof(kRadii) / sizeof(kRadii[0]);
 
@@ -325,7 +326,7 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     CK(cudaEventCreateWithFlags(&s.ev_boundary, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_halo, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
-    s.ev_all.resize(4 * H->scales.size() + 2);
+    s.ev_all.resize(kEvPerScale * H->scales.size() + 2);
     for (auto& e : s.ev_all) CK(cudaEventCreate(&e));
     s.ev_time = s.ev_all.data();
     CK(cudaMalloc(&s.dI, (size_t)s.voxels));
@@ -540,6 +541,23 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
 // neighbours.  Slab k sends its lowest `halo` own planes down and its highest
 // `halo` own planes up, and receives the matching planes into the halo regions
 // of its Fxy buffer.  All calls of all local slabs sit in one NCCL group.
+// A view of planes [cz0, cz1) of a slab for the z pass and the Hessian / eigen stage: same
+// buffers, outputs offset to the view's first plane, F and Fxy ranges clipped to what the slab
+// holds (own planes plus exchanged halo).  The xy-smoothed planes keep the slab's layout.
+Slab slab_view(frangi_gpu* H, const Slab& s, int cz0, int cz1)
+{
+    Slab v = s;
+    v.zb = cz0; v.ze = cz1;
+    v.fb = std::max(cz0 - 2, s.fb); v.fe = std::min(cz1 + 2, s.fe);
+    v.xb = std::max(v.fb - H->rz_max, s.xb); v.xe = std::min(v.fe + H->rz_max, s.xe);
+    v.dFxy = s.dFxy + (size_t)(v.xb - s.xb) * H->fplane;
+    const size_t off = (size_t)(cz0 - s.zb) * H->w * H->h;
+    v.dJ = s.dJ + off; v.dVx = s.dVx + off; v.dVy = s.dVy + off; v.dVz = s.dVz + off;
+    if (s.dScale) v.dScale = s.dScale + off;
+    if (s.dDir) v.dDir = s.dDir + off;
+    return v;
+}
+
 // Local-copy form (every slab lives in this process; used when device ids repeat or
 // FRANGI_GPU_FLAG_LOCAL_HALO is set): each slab PULLS its halo planes from its neighbours'
 // boundary planes with peer copies on its comm stream, after both its own and the
@@ -612,7 +630,7 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
     for (size_t k = 0; k < H->slabs.size(); ++k) {
         Slab& s = H->slabs[k];
         CK(cudaSetDevice(s.dev));
-        s.ev_time = s.ev_all.data() + (size_t)ev_set * (4 * S + 2);
+        s.ev_time = s.ev_all.data() + (size_t)ev_set * (kEvPerScale * S + 2);
         s.hMinMax[0] = 0x7f7fffff;            // FLT_MAX  (frangi.cpp:176)
         s.hMinMax[1] = (int)0xff7fffffu;      // -FLT_MAX (frangi.cpp:177)
         CK(cudaMemcpyAsync(s.dMinMax, s.hMinMax, 2 * sizeof(int), cudaMemcpyHostToDevice, s.s_main));
@@ -644,27 +662,52 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
             for (size_t k = 0; k < H->slabs.size(); ++k) {
                 Slab& s = H->slabs[k];
                 CK(cudaSetDevice(s.dev));
+                cudaEvent_t* ev = s.ev_time + kEvPerScale * si;
                 CK(cudaEventRecord(s.ev_halo, s.s_comm));
                 const int nz = s.ze - s.zb;
                 if (nz > 2 * halo) RC(launch_xy(H, s, sp, I_own[k], s.zb + halo, s.ze - halo));
-                CK(cudaEventRecord(s.ev_time[1 + 4 * si], s.s_main));
+                CK(cudaEventRecord(ev[1], s.s_main));
+                // Planes at least `halo` away from a neighbour need nothing from it: their z pass and
+                // Hessian / eigen stage run while the exchange is still in flight; the planes next to
+                // a neighbour follow once the halo has arrived.
+                const int lo_n = s.index > 0 ? std::min(halo, nz) : 0;
+                const int hi_n = s.index < H->nslabs_total - 1 ? std::min(halo, nz - lo_n) : 0;
+                const int zi0 = s.zb + lo_n, zi1 = s.ze - hi_n;
+                if (zi1 > zi0) {
+                    Slab v = slab_view(H, s, zi0, zi1);
+                    RC(launch_z(H, v, sp));
+                    CK(cudaEventRecord(ev[2], s.s_main));
+                    RC(launch_voxel(H, v, sp, si));
+                } else {
+                    CK(cudaEventRecord(ev[2], s.s_main));
+                }
+                CK(cudaEventRecord(ev[3], s.s_main));
                 CK(cudaStreamWaitEvent(s.s_main, s.ev_halo, 0));
-                CK(cudaEventRecord(s.ev_time[2 + 4 * si], s.s_main));
+                CK(cudaEventRecord(ev[4], s.s_main));
+                if (lo_n > 0) {
+                    Slab v = slab_view(H, s, s.zb, zi0);
+                    RC(launch_z(H, v, sp));
+                    RC(launch_voxel(H, v, sp, si));
+                }
+                if (hi_n > 0) {
+                    Slab v = slab_view(H, s, zi1, s.ze);
+                    RC(launch_z(H, v, sp));
+                    RC(launch_voxel(H, v, sp, si));
+                }
+                CK(cudaEventRecord(ev[5], s.s_main));
             }
         } else {
             Slab& s = H->slabs[0];
             CK(cudaSetDevice(s.dev));
+            cudaEvent_t* ev = s.ev_time + kEvPerScale * si;
             RC(launch_xy(H, s, sp, I_own[0], s.zb, s.ze));
-            CK(cudaEventRecord(s.ev_time[1 + 4 * si], s.s_main));
-            CK(cudaEventRecord(s.ev_time[2 + 4 * si], s.s_main));
-        }
-        for (size_t k = 0; k < H->slabs.size(); ++k) {
-            Slab& s = H->slabs[k];
-            CK(cudaSetDevice(s.dev));
+            CK(cudaEventRecord(ev[1], s.s_main));
             RC(launch_z(H, s, sp));
-            CK(cudaEventRecord(s.ev_time[3 + 4 * si], s.s_main));
+            CK(cudaEventRecord(ev[2], s.s_main));
             RC(launch_voxel(H, s, sp, si));
-            CK(cudaEventRecord(s.ev_time[4 + 4 * si], s.s_main));
+            CK(cudaEventRecord(ev[3], s.s_main));
+            CK(cudaEventRecord(ev[4], s.s_main));
+            CK(cudaEventRecord(ev[5], s.s_main));
         }
     }
     // global Jmin / Jmax across slabs, then the 8-bit normalisation
@@ -709,7 +752,7 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
         g_launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(s.hMinMax, s.dMinMax, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.s_main));
-        CK(cudaEventRecord(s.ev_time[4 * S + 1], s.s_main));
+        CK(cudaEventRecord(s.ev_time[kEvPerScale * S + 1], s.s_main));
     }
     H->ran = true;
     return 0;
@@ -743,22 +786,23 @@ int collect(frangi_gpu* H, float* Jmin, float* Jmax)
     int nsets = (int)std::min<long long>(H->runs_recorded, H->timing_depth);
     if (H->last_streamed) {
         float t;
-        CK(cudaEventElapsedTime(&t, s0.ev_all[0], s0.ev_all[4 * S + 1]));
+        CK(cudaEventElapsedTime(&t, s0.ev_all[0], s0.ev_all[kEvPerScale * S + 1]));
         H->last_ms[5] = t;
         nsets = 0;
     }
     for (int r = 0; r < nsets; ++r) {
-        const cudaEvent_t* ev = s0.ev_all.data() + (size_t)r * (4 * S + 2);
+        const cudaEvent_t* ev = s0.ev_all.data() + (size_t)r * (kEvPerScale * S + 2);
         float t;
         for (int si = 0; si < S; ++si) {
-            cudaEvent_t prev = si == 0 ? ev[0] : ev[4 * si];
-            CK(cudaEventElapsedTime(&t, prev, ev[1 + 4 * si])); H->last_ms[0] += t;
-            CK(cudaEventElapsedTime(&t, ev[1 + 4 * si], ev[2 + 4 * si])); H->last_ms[4] += t;
-            CK(cudaEventElapsedTime(&t, ev[2 + 4 * si], ev[3 + 4 * si])); H->last_ms[1] += t;
-            CK(cudaEventElapsedTime(&t, ev[3 + 4 * si], ev[4 + 4 * si])); H->last_ms[2] += t;
+            const cudaEvent_t* e = ev + kEvPerScale * si;     // e[0] = end of the previous scale (or run start)
+            CK(cudaEventElapsedTime(&t, e[0], e[1])); H->last_ms[0] += t;   // xy smoothing
+            CK(cudaEventElapsedTime(&t, e[1], e[2])); H->last_ms[1] += t;   // z smoothing (interior part when multi-slab)
+            CK(cudaEventElapsedTime(&t, e[2], e[3])); H->last_ms[2] += t;   // Hessian / eigen (interior part)
+            CK(cudaEventElapsedTime(&t, e[3], e[4])); H->last_ms[4] += t;   // exposed halo wait
+            CK(cudaEventElapsedTime(&t, e[4], e[5])); H->last_ms[2] += t;   // boundary planes (z pass + Hessian / eigen)
         }
-        CK(cudaEventElapsedTime(&t, ev[4 * S], ev[4 * S + 1])); H->last_ms[3] += t;
-        CK(cudaEventElapsedTime(&t, ev[0], ev[4 * S + 1])); H->last_ms[5] += t;
+        CK(cudaEventElapsedTime(&t, ev[kEvPerScale * S], ev[kEvPerScale * S + 1])); H->last_ms[3] += t;
+        CK(cudaEventElapsedTime(&t, ev[0], ev[kEvPerScale * S + 1])); H->last_ms[5] += t;
     }
     if (nsets > 0)
         for (int i = 0; i < 6; ++i) H->last_ms[i] /= (float)nsets;
@@ -872,7 +916,7 @@ int run_streamed(frangi_gpu* H, const uint8_t* I_host, float* J, uint8_t* Vx, ui
     CK(cudaGetLastError());
     if (J8) CK(cudaMemcpyAsync(J8, s.dJ8, (size_t)s.voxels, cudaMemcpyDeviceToHost, s.s_main));
     CK(cudaMemcpyAsync(s.hMinMax, s.dMinMax, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.s_main));
-    CK(cudaEventRecord(s.ev_time[4 * S + 1], s.s_main));
+    CK(cudaEventRecord(s.ev_time[kEvPerScale * S + 1], s.s_main));
     H->ran = true;
     return 0;
 }
@@ -1125,7 +1169,7 @@ FRANGI_API int frangi_gpu_timing_depth(frangi_gpu_t* H, int depth)
 {
     if (!H || depth < 1 || depth > 4096) return fail(FRANGI_GPU_EINVAL, "timing depth must be 1..4096");
     RC(sync_all(H));
-    const size_t per = 4 * H->scales.size() + 2;
+    const size_t per = kEvPerScale * H->scales.size() + 2;
     for (auto& s : H->slabs) {
         CK(cudaSetDevice(s.dev));
         while (s.ev_all.size() < per * (size_t)depth) {
