@@ -509,9 +509,10 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
     p.n_zface = (long long)H->w * H->h * p.nzf;
     p.n_yface = (long long)H->w * p.nyf * p.nz;
     p.n_xface = (long long)p.nxf * H->h * p.nz;
-    const long long nshell = p.n_zface + p.n_yface + p.n_xface;
     long long nblocks = tiles * nzc;
-    if (H->w < 5 || H->h < 5 || H->l < 5) nblocks = 0;   // no voxel is two steps away from every face
+    if (H->w < 5 || H->h < 5 || H->l < 5) nblocks = 0;   // volumes this thin go to the shell kernel entirely
+    if (nblocks > 0) { p.nzf = 0; p.n_zface = 0; }       // the tile kernels handle the z faces themselves
+    const long long nshell = p.n_zface + p.n_yface + p.n_xface;
     if (nblocks > 0x7fffffffLL || (nshell + 127) / 128 > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
     if (D) return launch_voxel_t<2>(p, nblocks, nshell, s.s_main);
     if (si == 0) return launch_voxel_t<0>(p, nblocks, nshell, s.s_main);

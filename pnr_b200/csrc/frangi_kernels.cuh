@@ -682,69 +682,130 @@ __device__ __noinline__ float voxel_update(const VoxelParams& p, long long i, co
     return jold;
 }
 
-// Second differences of four consecutive x voxels of one tile row, interior form, as two packed
-// pairs (voxels 0,1 and 2,3).  `o` = tile entry of (x - 2, y) of the first voxel; P0 = plane z,
-// Pm1/Pp1 = z-+1, Pm2/Pp2 = z-+2 of the shared-memory ring.
-__device__ __forceinline__ void quad_hessians(const float* P0, const float* Pm1, const float* Pp1, const float* Pm2,
-                                              const float* Pp2, int o, float qs, float2* Hxx, float2* Hxy,
+// The planes and factors the z direction of the second differences needs at centre plane z,
+// identical for every voxel of the plane (so they are set up once per plane, uniformly):
+//   zl = max(z-1, 0), zh = min(z+1, l-1); first differences in x / y are taken on planes zl, zh;
+//   dz(zh) = sh * (F[clamp(zh+1)] - F[clamp(zh-1)]), dz(zl) = sl * (F[clamp(zl+1)] - F[clamp(zl-1)]),
+//   with the face scale 1 on a volume face and 0.5 inside (frangi.cpp:308-310); the second
+//   difference applies sz = face scale of z itself (frangi.cpp:315-317), then * sigma^2.
+// Two steps away from the z faces this reduces to the closed interior form (general == false).
+struct ZPlanes {              // plane fields are float offsets into the shared-memory ring
+    int P0;                   // plane z
+    int Pzl, Pzh;             // planes zl, zh
+    int Pa, Pb;               // planes clamp(zh+1), clamp(zh-1)
+    int Pc, Pd;               // planes clamp(zl+1), clamp(zl-1)
+    float sh, sl;
+    float qs;                 // sigma^2 / 4          in-plane terms
+    float qz;                 // 0.5 * sz * sigma^2   xz, yz
+    float qzz;                // sz * sigma^2         zz
+    bool general;
+};
+
+// interior planes (2 <= z <= l-3): only the five ring offsets and sigma^2/4 are needed
+template <class TILE>
+__device__ __forceinline__ ZPlanes z_planes_interior(int z, float sigma2)
+{
+    ZPlanes zp;
+    zp.P0 = (z % TILE::SLOTS) * TILE::PLANE;
+    zp.Pzl = ((z - 1) % TILE::SLOTS) * TILE::PLANE; zp.Pzh = ((z + 1) % TILE::SLOTS) * TILE::PLANE;
+    zp.Pa = ((z + 2) % TILE::SLOTS) * TILE::PLANE; zp.Pd = ((z - 2) % TILE::SLOTS) * TILE::PLANE;
+    zp.Pb = zp.P0; zp.Pc = zp.P0;
+    zp.sh = zp.sl = 0.5f;
+    zp.qs = 0.25f * sigma2; zp.qz = zp.qs; zp.qzz = 0.5f * sigma2;
+    zp.general = false;
+    return zp;
+}
+
+template <class TILE>
+__device__ __forceinline__ ZPlanes z_planes(int z, int l, float sigma2)
+{
+    auto plane = [&](int q) { return (clampi(q, 0, l - 1) % TILE::SLOTS) * TILE::PLANE; };
+    const int zl = max(z - 1, 0), zh = min(z + 1, l - 1);
+    const float sz = face_scale(z, l);
+    ZPlanes zp;
+    zp.P0 = plane(z); zp.Pzl = plane(zl); zp.Pzh = plane(zh);
+    zp.Pa = plane(zh + 1); zp.Pb = plane(zh - 1); zp.Pc = plane(zl + 1); zp.Pd = plane(zl - 1);
+    zp.sh = face_scale(zh, l); zp.sl = face_scale(zl, l);
+    zp.qs = 0.25f * sigma2; zp.qz = 0.5f * sz * sigma2; zp.qzz = sz * sigma2;
+    zp.general = z < 2 || z > l - 3;
+    return zp;
+}
+
+// Second differences of four consecutive x voxels of one tile row (x and y interior), as two
+// packed pairs (voxels 0,1 and 2,3).  `o` = tile entry of (x - 2, y) of the first voxel.
+// (hi - mid) - (mid - lo), then * sigma^2/4: FADD2 / FMUL2 round each lane exactly like the scalar
+// __fsub_rn / __fmul_rn chain of the reference's two passes (halving is exact and commutes with the
+// roundings; no multiply feeds an add, so nothing can fuse).
+template <bool ZGEN>
+__device__ __forceinline__ void quad_hessians(const float* ring, const ZPlanes& zp, int o, float2* Hxx, float2* Hxy,
                                               float2* Hxz, float2* Hyy, float2* Hyz, float2* Hzz)
 {
     using T = HessTile;
-                    // plane z: rows y-1, y, y+1 over x-2 .. x+5; rows y-2, y+2 over x .. x+3
-                    float a[8], b[8], c[8];
-                    *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(P0 + o - T::PW);
-                    *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(P0 + o - T::PW + 4);
-                    *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(P0 + o);
-                    *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(P0 + o + 4);
-                    *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(P0 + o + T::PW);
-                    *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(P0 + o + T::PW + 4);
-                    float t2[4], u2[4];
-                    *reinterpret_cast<float2*>(t2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 2);
-                    *reinterpret_cast<float2*>(t2 + 2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 4);
-                    *reinterpret_cast<float2*>(u2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 2);
-                    *reinterpret_cast<float2*>(u2 + 2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 4);
-                    float k2[4], l2[4];
-                    *reinterpret_cast<float2*>(k2) = *reinterpret_cast<const float2*>(Pm2 + o + 2);
-                    *reinterpret_cast<float2*>(k2 + 2) = *reinterpret_cast<const float2*>(Pm2 + o + 4);
-                    *reinterpret_cast<float2*>(l2) = *reinterpret_cast<const float2*>(Pp2 + o + 2);
-                    *reinterpret_cast<float2*>(l2 + 2) = *reinterpret_cast<const float2*>(Pp2 + o + 4);
-                    // planes z-1, z+1: row y over x-1 .. x+4 (loaded as x-2 .. x+5), rows y-1, y+1 over x .. x+3
-                    float mm[8], nn[8], mu[4], md[4], nu[4], nd[4];
-                    *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(Pm1 + o);
-                    *reinterpret_cast<float4*>(mm + 4) = *reinterpret_cast<const float4*>(Pm1 + o + 4);
-                    *reinterpret_cast<float4*>(nn) = *reinterpret_cast<const float4*>(Pp1 + o);
-                    *reinterpret_cast<float4*>(nn + 4) = *reinterpret_cast<const float4*>(Pp1 + o + 4);
-                    *reinterpret_cast<float2*>(mu) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 2);
-                    *reinterpret_cast<float2*>(mu + 2) = *reinterpret_cast<const float2*>(Pm1 + o - T::PW + 4);
-                    *reinterpret_cast<float2*>(md) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 2);
-                    *reinterpret_cast<float2*>(md + 2) = *reinterpret_cast<const float2*>(Pm1 + o + T::PW + 4);
-                    *reinterpret_cast<float2*>(nu) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 2);
-                    *reinterpret_cast<float2*>(nu + 2) = *reinterpret_cast<const float2*>(Pp1 + o - T::PW + 4);
-                    *reinterpret_cast<float2*>(nd) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 2);
-                    *reinterpret_cast<float2*>(nd + 2) = *reinterpret_cast<const float2*>(Pp1 + o + T::PW + 4);
-                    const float2 qs2 = make_float2(qs, qs);
-                    // (hi - mid) - (mid - lo), then * sigma^2/4: FADD2 / FMUL2 round each lane exactly like
-                    // the scalar __fsub_rn / __fmul_rn chain (no multiply feeds an add, so nothing can fuse)
-    #define PAIR(arr, i) make_float2((arr)[(i)], (arr)[(i) + 1])
-    #define DD(hi, mid, lo) vmul(vsub(vsub(hi, mid), vsub(mid, lo)), qs2)
-    #define DX(hi1, lo1, hi0, lo0) vmul(vsub(vsub(hi1, lo1), vsub(hi0, lo0)), qs2)
-    #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const int j = 2 * g;
-                        const float2 f0 = PAIR(b, j + 2);
-                        Hxx[g] = DD(PAIR(b, j + 4), f0, PAIR(b, j));
-                        Hyy[g] = DD(PAIR(u2, j), f0, PAIR(t2, j));
-                        Hzz[g] = DD(PAIR(l2, j), f0, PAIR(k2, j));
-                        // the x+-1 taps sit at odd register offsets of the 128-bit loads: scalar form, no re-pairing moves
-                        Hxy[g].x = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 3], c[j + 1]), __fsub_rn(a[j + 3], a[j + 1])), qs);
-                        Hxy[g].y = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 4], c[j + 2]), __fsub_rn(a[j + 4], a[j + 2])), qs);
-                        Hxz[g].x = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 3], nn[j + 1]), __fsub_rn(mm[j + 3], mm[j + 1])), qs);
-                        Hxz[g].y = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 4], nn[j + 2]), __fsub_rn(mm[j + 4], mm[j + 2])), qs);
-                        Hyz[g] = DX(PAIR(nd, j), PAIR(nu, j), PAIR(md, j), PAIR(mu, j));
-                    }
-    #undef PAIR
-    #undef DD
-    #undef DX
+    const float* P0 = ring + zp.P0;
+    // plane z: rows y-1, y, y+1 over x-2 .. x+5; rows y-2, y+2 over x .. x+3
+    float a[8], b[8], c[8];
+    *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(P0 + o - T::PW);
+    *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(P0 + o - T::PW + 4);
+    *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(P0 + o);
+    *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(P0 + o + 4);
+    *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(P0 + o + T::PW);
+    *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(P0 + o + T::PW + 4);
+    float t2[4], u2[4];
+    *reinterpret_cast<float2*>(t2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 2);
+    *reinterpret_cast<float2*>(t2 + 2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 4);
+    *reinterpret_cast<float2*>(u2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 2);
+    *reinterpret_cast<float2*>(u2 + 2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 4);
+    // own column on the planes of the z second difference
+    float pa[4], pd[4], pb[4], pc[4];
+    *reinterpret_cast<float2*>(pa) = *reinterpret_cast<const float2*>(ring + zp.Pa + o + 2);
+    *reinterpret_cast<float2*>(pa + 2) = *reinterpret_cast<const float2*>(ring + zp.Pa + o + 4);
+    *reinterpret_cast<float2*>(pd) = *reinterpret_cast<const float2*>(ring + zp.Pd + o + 2);
+    *reinterpret_cast<float2*>(pd + 2) = *reinterpret_cast<const float2*>(ring + zp.Pd + o + 4);
+    if (ZGEN) {
+        *reinterpret_cast<float2*>(pb) = *reinterpret_cast<const float2*>(ring + zp.Pb + o + 2);
+        *reinterpret_cast<float2*>(pb + 2) = *reinterpret_cast<const float2*>(ring + zp.Pb + o + 4);
+        *reinterpret_cast<float2*>(pc) = *reinterpret_cast<const float2*>(ring + zp.Pc + o + 2);
+        *reinterpret_cast<float2*>(pc + 2) = *reinterpret_cast<const float2*>(ring + zp.Pc + o + 4);
+    }
+    // planes zl, zh: row y over x-1 .. x+4 (loaded as x-2 .. x+5), rows y-1, y+1 over x .. x+3
+    float mm[8], nn[8], mu[4], md[4], nu[4], nd[4];
+    *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(ring + zp.Pzl + o);
+    *reinterpret_cast<float4*>(mm + 4) = *reinterpret_cast<const float4*>(ring + zp.Pzl + o + 4);
+    *reinterpret_cast<float4*>(nn) = *reinterpret_cast<const float4*>(ring + zp.Pzh + o);
+    *reinterpret_cast<float4*>(nn + 4) = *reinterpret_cast<const float4*>(ring + zp.Pzh + o + 4);
+    *reinterpret_cast<float2*>(mu) = *reinterpret_cast<const float2*>(ring + zp.Pzl + o - T::PW + 2);
+    *reinterpret_cast<float2*>(mu + 2) = *reinterpret_cast<const float2*>(ring + zp.Pzl + o - T::PW + 4);
+    *reinterpret_cast<float2*>(md) = *reinterpret_cast<const float2*>(ring + zp.Pzl + o + T::PW + 2);
+    *reinterpret_cast<float2*>(md + 2) = *reinterpret_cast<const float2*>(ring + zp.Pzl + o + T::PW + 4);
+    *reinterpret_cast<float2*>(nu) = *reinterpret_cast<const float2*>(ring + zp.Pzh + o - T::PW + 2);
+    *reinterpret_cast<float2*>(nu + 2) = *reinterpret_cast<const float2*>(ring + zp.Pzh + o - T::PW + 4);
+    *reinterpret_cast<float2*>(nd) = *reinterpret_cast<const float2*>(ring + zp.Pzh + o + T::PW + 2);
+    *reinterpret_cast<float2*>(nd + 2) = *reinterpret_cast<const float2*>(ring + zp.Pzh + o + T::PW + 4);
+    const float qs = zp.qs, qz = ZGEN ? zp.qz : zp.qs;
+    const float2 qs2 = make_float2(qs, qs), qz2 = make_float2(qz, qz);
+#define PAIR(arr, i) make_float2((arr)[(i)], (arr)[(i) + 1])
+#define DD(hi, mid, lo) vmul(vsub(vsub(hi, mid), vsub(mid, lo)), qs2)
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int j = 2 * g;
+        const float2 f0 = PAIR(b, j + 2);
+        Hxx[g] = DD(PAIR(b, j + 4), f0, PAIR(b, j));
+        Hyy[g] = DD(PAIR(u2, j), f0, PAIR(t2, j));
+        if (ZGEN)
+            Hzz[g] = vmul(vsub(vmul(make_float2(zp.sh, zp.sh), vsub(PAIR(pa, j), PAIR(pb, j))),
+                               vmul(make_float2(zp.sl, zp.sl), vsub(PAIR(pc, j), PAIR(pd, j)))),
+                          make_float2(zp.qzz, zp.qzz));
+        else
+            Hzz[g] = DD(PAIR(pa, j), f0, PAIR(pd, j));
+        // the x+-1 taps sit at odd register offsets of the 128-bit loads: scalar form, no re-pairing moves
+        Hxy[g].x = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 3], c[j + 1]), __fsub_rn(a[j + 3], a[j + 1])), qs);
+        Hxy[g].y = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 4], c[j + 2]), __fsub_rn(a[j + 4], a[j + 2])), qs);
+        Hxz[g].x = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 3], nn[j + 1]), __fsub_rn(mm[j + 3], mm[j + 1])), qz);
+        Hxz[g].y = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 4], nn[j + 2]), __fsub_rn(mm[j + 4], mm[j + 2])), qz);
+        Hyz[g] = vmul(vsub(vsub(PAIR(nd, j), PAIR(nu, j)), vsub(PAIR(md, j), PAIR(mu, j))), qz2);
+    }
+#undef PAIR
+#undef DD
 }
 
 template <int MODE, bool BRIGHT = false>
@@ -761,9 +822,9 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
     const int bz = bid / p.nty;
     const int x0 = bx * T::TX - 2, y0 = by * T::TY - 2;       // global coordinates of tile entry (0, 0)
     const int w = p.f.w, h = p.f.h, l = p.f.l;
-    // centre planes of this CTA, clipped to the interior 2 .. l-3
-    const int zs = max(p.z_begin + bz * p.zchunk, 2);
-    const int ze = min(min(p.z_begin + (bz + 1) * p.zchunk, p.z_begin + p.nz), l - 2);
+    // centre planes of this CTA (z faces included: see ZPlanes; x and y faces belong to K3b)
+    const int zs = p.z_begin + bz * p.zchunk;
+    const int ze = min(zs + p.zchunk, p.z_begin + p.nz);
     if (zs >= ze) return;
 
     // staging map: the tile as 8-byte units (x0 is even, so every unit is 8-byte aligned in global memory);
@@ -784,6 +845,7 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
     }
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     auto fetch = [&](int plane) {             // asynchronous global -> shared copy of one plane's tile
+        if (plane < 0 || plane > l - 1) return;   // beyond a z face: the face rules never read it
         const float* __restrict__ src = p.f.F + (long long)(plane - p.f.base) * p.f.fplane;
         const unsigned dst = ring_s + ((plane % T::SLOTS) * T::PLANE + 2 * tid) * 4;
 #pragma unroll
@@ -805,7 +867,6 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
     for (int j = 0; j < 4; ++j) m[j] = xq + j >= 2 && xq + j <= w - 3;
     const bool any_x = m[0] || m[1] || m[2] || m[3];
     const bool all_x = m[0] && m[1] && m[2] && m[3] && p.vec_ok;
-    const float qs = 0.25f * p.k.sigma2;
     float vmin = 3.4e38f, vmax = 0.0f;
 
     for (int z = zs; z < ze; ++z) {
@@ -813,11 +874,7 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
         __syncthreads();                          // plane z+2 visible; everyone is done with plane z-3's slot
         if (z + 1 < ze) fetch(z + 3);             // lands in that slot while plane z is processed
 
-        const float* P0 = ring + (z % T::SLOTS) * T::PLANE;
-        const float* Pm1 = ring + ((z - 1) % T::SLOTS) * T::PLANE;
-        const float* Pp1 = ring + ((z + 1) % T::SLOTS) * T::PLANE;
-        const float* Pm2 = ring + ((z - 2) % T::SLOTS) * T::PLANE;
-        const float* Pp2 = ring + ((z + 2) % T::SLOTS) * T::PLANE;
+        const bool z_general = z < 2 || z > l - 3;
 
 #pragma unroll 1
         for (int half = 0; half < T::RPT; ++half) {
@@ -826,7 +883,8 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
             if (y < 2 || y > h - 3 || !any_x) continue;
             // second differences of the quad as two packed pairs (voxels 0,1 and 2,3)
             float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
-            quad_hessians(P0, Pm1, Pp1, Pm2, Pp2, (yl + 2) * T::PW + 4 * tx, qs, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+            if (z_general) quad_hessians<true>(ring, z_planes<T>(z, l, p.k.sigma2), (yl + 2) * T::PW + 4 * tx, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+            else quad_hessians<false>(ring, z_planes_interior<T>(z, p.k.sigma2), (yl + 2) * T::PW + 4 * tx, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
 
             const long long i0 = ((long long)(z - p.z_begin) * h + y) * w + xq;
             if (MODE == 2 || !all_x) {            // stage dump; quads that straddle an x face; unaligned widths
@@ -962,8 +1020,8 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     const int bz = bid / p.nty;
     const int x0 = bx * T::TX - 2, y0 = by * T::TY - 2;
     const int w = p.f.w, h = p.f.h, l = p.f.l;
-    const int zs = max(p.z_begin + bz * p.zchunk, 2);
-    const int ze = min(min(p.z_begin + (bz + 1) * p.zchunk, p.z_begin + p.nz), l - 2);
+    const int zs = p.z_begin + bz * p.zchunk;
+    const int ze = min(zs + p.zchunk, p.z_begin + p.nz);
     if (zs >= ze) return;
     if (tid == 0) s_tail = 0;
 
@@ -982,6 +1040,7 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     }
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     auto fetch = [&](int plane) {
+        if (plane < 0 || plane > l - 1) return;   // beyond a z face: the face rules never read it
         const float* __restrict__ src = p.f.F + (long long)(plane - p.f.base) * p.f.fplane;
         const unsigned dst = ring_s + ((plane % T::SLOTS) * T::PLANE + 2 * tid) * 4;
 #pragma unroll
@@ -1001,7 +1060,6 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     for (int j = 0; j < 4; ++j) m[j] = xq + j >= 2 && xq + j <= w - 3;
     const bool any_x = m[0] || m[1] || m[2] || m[3];
     const bool vec_j = p.vec_ok && xq + 3 < w;
-    const float qs = 0.25f * p.k.sigma2;
     float vmax = 0.0f;
     unsigned head = 0;        // entries [head, tail) are pending; every thread carries the same value
     // The stored response of the thread's quad is fetched one plane ahead, so that the load is in
@@ -1060,11 +1118,7 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                          // plane z+2 visible; nobody reads plane z-3's slot or drains any more
         if (z + 1 < ze) fetch(z + 3);
-        const float* P0 = ring + (z % T::SLOTS) * T::PLANE;
-        const float* Pm1 = ring + ((z - 1) % T::SLOTS) * T::PLANE;
-        const float* Pp1 = ring + ((z + 1) % T::SLOTS) * T::PLANE;
-        const float* Pm2 = ring + ((z - 2) % T::SLOTS) * T::PLANE;
-        const float* Pp2 = ring + ((z + 2) % T::SLOTS) * T::PLANE;
+        const bool z_general = z < 2 || z > l - 3;
         const int yl = ty;                        // one tile row per warp
         const int y = by * T::TY + yl;
         // ---- phase A: second differences, the diagonal-sum test, append survivors ----
@@ -1073,7 +1127,8 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         const float jold[4] = { jnext[0], jnext[1], jnext[2], jnext[3] };
         if (row_ok && z + 1 < ze) load_j(z + 1);
         if (row_ok) {
-            quad_hessians(P0, Pm1, Pp1, Pm2, Pp2, (yl + 2) * T::PW + 4 * tx, qs, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+            if (z_general) quad_hessians<true>(ring, z_planes<T>(z, l, p.k.sigma2), (yl + 2) * T::PW + 4 * tx, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+            else quad_hessians<false>(ring, z_planes_interior<T>(z, p.k.sigma2), (yl + 2) * T::PW + 4 * tx, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 const float2 sxy = vadd(Hxx[g], Hyy[g]), sxz = vadd(Hxx[g], Hzz[g]), syz = vadd(Hyy[g], Hzz[g]);
