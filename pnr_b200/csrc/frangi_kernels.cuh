@@ -287,7 +287,7 @@ __device__ __forceinline__ void xy_fma_ypass(const float* s_ring, const GaussTap
 }
 
 template <int L>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (L <= 9 ? 3 : 2))
 gauss_xy_fma_kernel(const __grid_constant__ XYParams p, const __grid_constant__ GaussTaps taps)
 {
     using C = XYFmaCfg<L>;
