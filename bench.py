@@ -91,6 +91,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--pageable", action="store_true",
+                    help="e2e with ordinary (pageable) host buffers, as an unmodified caller would pass them")
     ap.add_argument("--verify", action="store_true",
                     help="N > 1: check every rank's slab of J / V bit for bit against a one-GPU run of the whole volume on rank 0")
     return ap.parse_args()
@@ -376,14 +378,26 @@ def run_ours(a, sigmas, w, h, l):
     # ---- end to end through the C-ABI call with host buffers ----------------------
     e2e = None
     if not a.no_e2e:
-        hJ = PinnedBuffer((nz, h, w), np.float32)
-        hV = [PinnedBuffer((nz, h, w), np.uint8) for _ in range(3)]
+        if a.pageable:
+            class _Plain:
+                def __init__(self, shape, dt):
+                    self.array = np.empty(shape, dt)
+                    self.array.fill(0)          # touch the pages
+                def free(self):
+                    self.array = None
+            hJ = _Plain((nz, h, w), np.float32)
+            hV = [_Plain((nz, h, w), np.uint8) for _ in range(3)]
+            hIe = np.array(hI.array)
+        else:
+            hJ = PinnedBuffer((nz, h, w), np.float32)
+            hV = [PinnedBuffer((nz, h, w), np.uint8) for _ in range(3)]
+            hIe = hI.array
         k_e2e = a.e2e_steps or min(a.steps, 5)
-        plan.run(hI.array, J=hJ.array, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array)   # warm-up
+        plan.run(hIe, J=hJ.array, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array)   # warm-up
         barrier()
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            r = plan.run(hI.array, J=hJ.array, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array)
+            r = plan.run(hIe, J=hJ.array, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         te = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -393,10 +407,11 @@ def run_ours(a, sigmas, w, h, l):
         e2e = {"value": total_vox * k_e2e / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(total_vox), "d2h_bytes_per_step": int(total_vox * 7 + 8 * world),
                "steps": k_e2e, "ms_per_step": 1e3 * dt / k_e2e,
-               "call": "frangi_gpu_run(I_host -> J_host f32, Jmin, Jmax, Vx, Vy, Vz host u8), pinned host buffers",
+               "call": "frangi_gpu_run(I_host -> J_host f32, Jmin, Jmax, Vx, Vy, Vz host u8), "
+                       + ("pageable" if a.pageable else "pinned") + " host buffers",
                "jmax": float(r["Jmax"])}
         # the same call as the caller really needs it (J is freed at once, Advantra_plugin.cpp:2514): J8 + V only
-        if world == 1:
+        if world == 1 and not a.pageable:
             hJ8 = PinnedBuffer((nz, h, w), np.uint8)
             plan.run(hI.array, J=None, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array, J8=hJ8.array, want_J=False)
             barrier()
