@@ -10,6 +10,7 @@
 // the fused Hessian/eigen/vesselness/max kernel.
 #include "../../include/frangi_gpu.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -210,6 +211,8 @@ struct Slab {
     float* dJ = nullptr;
     uint8_t *dVx = nullptr, *dVy = nullptr, *dVz = nullptr, *dScale = nullptr, *dJ8 = nullptr;
     float* dDir = nullptr;
+    CUtensorMap tmF{}, tmFc{};   // TMA descriptors of dF: boxes of the full-eigen and of the compacting K3 kernel
+    bool has_tm = false;
     int* dMinMax = nullptr;
     int* hMinMax = nullptr;   // pinned
     cudaStream_t s_main = nullptr, s_comm = nullptr, s_h2d = nullptr, s_d2h = nullptr;
@@ -310,6 +313,33 @@ int plan_common(frangi_gpu* H, const float* sigmas, int nsig, float zdist, float
     return 0;
 }
 
+// TMA descriptor of a slab's F buffer seen as a (w, h, planes) float tensor with rows `fpitch` floats apart;
+// a box is one (PW x PH x 1) plane tile.  Columns >= w and rows >= h are outside the tensor, so the copy
+// engine zero-fills them (as it does for negative coordinates).  cuTensorMapEncodeTiled is a driver entry
+// point: it is fetched through the runtime, so the library has no link-time dependency on libcuda.
+int make_tile_map(CUtensorMap* tm, float* F, int w, int h, int planes, int fpitch, long long fplane, int box_w, int box_h)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(FRANGI_GPU_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t dims[3] = { (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes };
+    const cuuint64_t strides[2] = { (cuuint64_t)fpitch * 4, (cuuint64_t)fplane * 4 };
+    const cuuint32_t box[3] = { (cuuint32_t)box_w, (cuuint32_t)box_h, 1 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, F, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FRANGI_GPU_ECUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d volume", (int)r, w, h, planes);
+    return 0;
+}
+
 int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
 {
     s.dev = dev; s.index = index; s.zb = zb; s.ze = ze;
@@ -332,6 +362,11 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     CK(cudaMalloc(&s.dI, (size_t)s.voxels));
     CK(cudaMalloc(&s.dFxy, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
     CK(cudaMalloc(&s.dF, sizeof(float) * (size_t)H->fplane * (s.fe - s.fb)));
+    if (H->w >= 5 && H->h >= 5 && H->l >= 5) {   // thinner volumes go to the shell kernel entirely (launch_voxel)
+        RC(make_tile_map(&s.tmF, s.dF, H->w, H->h, s.fe - s.fb, H->fpitch, H->fplane, HessTile::PW, HessTile::PH));
+        RC(make_tile_map(&s.tmFc, s.dF, H->w, H->h, s.fe - s.fb, H->fpitch, H->fplane, HessTileC::PW, HessTileC::PH));
+        s.has_tm = true;
+    }
     CK(cudaMalloc(&s.dJ, sizeof(float) * (size_t)s.voxels));
     CK(cudaMalloc(&s.dVx, (size_t)s.voxels));
     CK(cudaMalloc(&s.dVy, (size_t)s.voxels));
@@ -486,20 +521,21 @@ int face_list(int n, int lo, int hi, int* out)
 int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* const* D = nullptr)
 {
     VoxelParams p;
+    p.tmap = s.tmF;
     p.f = make_fview(H, s);
     p.J = s.dJ; p.Vx = s.dVx; p.Vy = s.dVy; p.Vz = s.dVz;
     p.scale_idx = s.dScale; p.dir = s.dDir; p.voxels = s.voxels;
     for (int k = 0; k < 6; ++k) p.D[k] = D ? D[k] : nullptr;
     p.z_begin = s.zb; p.nz = s.ze - s.zb;
-    p.ntx = (H->w + HessTile::TX - 1) / HessTile::TX;
+    p.ntx = (H->w - 4 + HessTile::TX - 1) / HessTile::TX;    // tiles cover x in [2, w-2): the x faces belong to the shell
     p.nty = (H->h + HessTile::TY - 1) / HessTile::TY;
     // enough CTAs for a few waves of 148 SMs x 2 resident CTAs; each z chunk re-stages 4 planes
-    const long long tiles = (long long)p.ntx * p.nty;
+    const long long tiles = std::max<long long>(1, (long long)p.ntx * p.nty);   // (w < 5: no tile at all, see below)
     long long nzc = std::max<long long>(1, std::min<long long>((1184 + tiles - 1) / tiles, (p.nz + 7) / 8));
     p.zchunk = (int)((p.nz + nzc - 1) / nzc);
     nzc = (p.nz + p.zchunk - 1) / p.zchunk;
     p.scale = si; p.last_scale = si == (int)H->scales.size() - 1;
-    p.vec_ok = (H->w % 4 == 0);
+    p.vec_ok = (H->w % 2 == 0);
     p.minmax = s.dMinMax;
     p.k = make_consts(H, sp.sigma2);
     // the two-voxel shell next to the volume faces goes to the shell kernel
@@ -523,7 +559,8 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
         p.nty = (H->h + HessTileC::TY - 1) / HessTileC::TY;
         nblocks = (long long)p.ntx * p.nty * nzc;
         if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
-        constexpr int smem = HessTileC::SMEM_BYTES + HessQueue::BYTES;
+        constexpr int smem = HessQueue::SMEM_BYTES;
+        p.tmap = s.tmFc;
         static thread_local int configured_dev[64] = { 0 };
         int dev = 0;
         CK(cudaGetDevice(&dev));

@@ -18,6 +18,7 @@
 // rather than from the trigonometric formula, which keeps the vesselness well
 // inside the 1e-4 relative / 1e-6 absolute tolerance of BASELINE.json.
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only; the encoder is fetched at run time)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -610,6 +611,93 @@ __device__ __noinline__ Hess hessian_at_face(const Field& f, int x, int y, int z
 // minmax[1] = bits of max J (max over every value any scale leaves in J).  J >= 0, so the int
 // order of the bit patterns is the float order.
 // ---------------------------------------------------------------------------
+
+// ---- TMA tile staging (cp.async.bulk.tensor + mbarrier) ----------------------------------------
+// The K3 kernels stage one (PW x PH x 1) box of the smoothed volume F per plane with a single
+// instruction issued by one thread; the copy engine zero-fills whatever lies outside the tensor
+// (x, y < 0, x >= w, y >= h), which is exactly what the voxels next to a volume face need (they
+// never read those entries).  Completion is signalled on a shared-memory mbarrier per ring slot.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// The ring of TILE::SLOTS plane tiles of a z-marching CTA.  Plane `zs - 2 + n` lives in slot n % SLOTS;
+// its mbarrier completes phase n / SLOTS.  Planes beyond a z face are not fetched (the face rules never
+// read them) but still complete their phase, so the parity bookkeeping is uniform.  o[0..4] are the
+// float offsets of planes z-2 .. z+2, rotated once per plane (no modulo in the loop).
+template <class TILE>
+struct TileRing {
+    uint32_t ring_s, mbar_s;
+    int o[5];
+    uint32_t wbar, wpar;          // barrier / parity of the next plane to wait for (plane z + 2)
+    uint32_t ibar, idst;          // thread 0: barrier / destination of the next plane to issue
+    __device__ __forceinline__ void init(float* ring, uint64_t* mbar, int tid)
+    {
+        ring_s = smem_u32(ring); mbar_s = smem_u32(mbar);
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < TILE::SLOTS; ++k) mbar_init(mbar_s + 8 * k, 1);
+            mbar_init_fence();
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) o[k] = k * TILE::SLOT;
+        wbar = mbar_s; wpar = 0; ibar = mbar_s; idst = ring_s;
+    }
+    // thread 0 only: start the copy of `plane` (tile origin x0, y0) into the next slot
+    __device__ __forceinline__ void issue(const CUtensorMap* tm, int x0, int y0, int plane, int base, int l)
+    {
+        if (plane < 0 || plane > l - 1) mbar_arrive(ibar);
+        else {
+            mbar_expect_tx(ibar, TILE::PLANE * 4);
+            tma_load_3d(idst, tm, ibar, x0, y0, plane - base);
+        }
+        ibar += 8; idst += TILE::SLOT * 4;
+        if (ibar == mbar_s + 8 * TILE::SLOTS) { ibar = mbar_s; idst = ring_s; }
+    }
+    __device__ __forceinline__ void wait_next()
+    {
+        mbar_wait(wbar, wpar);
+        wbar += 8;
+        if (wbar == mbar_s + 8 * TILE::SLOTS) { wbar = mbar_s; wpar ^= 1u; }
+    }
+    __device__ __forceinline__ void rotate()
+    {
+        o[0] = o[1]; o[1] = o[2]; o[2] = o[3]; o[3] = o[4];
+        o[4] += TILE::SLOT;
+        if (o[4] == TILE::SLOTS * TILE::SLOT) o[4] = 0;
+    }
+};
+
 struct FView {
     const float* F;     // plane 0 = global plane base
     int w, h, l;
@@ -633,12 +721,15 @@ struct HessTile {
     static constexpr int TX = 128, TY = 16, RPT = HESS_RPT, NT = 32 * TY / RPT;
     static constexpr int PW = TX + 4;            // 132 floats per tile row (16-byte multiple)
     static constexpr int PH = TY + 4;
-    static constexpr int PLANE = PW * PH;        // 2640 floats
+    static constexpr int PLANE = PW * PH;        // 2640 floats: the TMA box
+    static constexpr int SLOT = (PLANE * 4 + 127) / 128 * 32;   // ring slot in floats (TMA destinations are 128-byte aligned)
     static constexpr int SLOTS = 6;
-    static constexpr int SMEM_BYTES = SLOTS * PLANE * 4;  // 63360
+    static constexpr int RING_BYTES = SLOTS * SLOT * 4;
+    static constexpr int SMEM_BYTES = RING_BYTES + SLOTS * 8;   // + one mbarrier per slot (63792)
 };
 
 struct VoxelParams {
+    CUtensorMap tmap;     // F as a (w, h, planes) tensor, box = the launching kernel's tile (PW x PH x 1)
     FView f;
     float* J;
     uint8_t* Vx;
@@ -653,7 +744,7 @@ struct VoxelParams {
     int ntx, nty;         // tiles along x and y (K3a)
     int scale;            // index of this scale
     int last_scale;
-    int vec_ok;           // w % 4 == 0: quads are aligned for 128-bit / 32-bit vector stores
+    int vec_ok;           // w % 2 == 0: the pairs of a quad (xq = 2 mod 4) are aligned for 64-bit / 16-bit vector accesses
     int* minmax;
     FrangiConsts k;
     // K3b: the face coordinates (deduplicated) and the three region sizes
@@ -701,14 +792,14 @@ struct ZPlanes {              // plane fields are float offsets into the shared-
     bool general;
 };
 
-// interior planes (2 <= z <= l-3): only the five ring offsets and sigma^2/4 are needed
-template <class TILE>
-__device__ __forceinline__ ZPlanes z_planes_interior(int z, float sigma2)
+// interior planes (2 <= z <= l-3): only the five ring offsets and sigma^2/4 are needed.
+// o[0..4] = ring offsets (floats) of planes z-2 .. z+2 (TileRing::o).
+__device__ __forceinline__ ZPlanes z_planes_interior(const int* o, float sigma2)
 {
     ZPlanes zp;
-    zp.P0 = (z % TILE::SLOTS) * TILE::PLANE;
-    zp.Pzl = ((z - 1) % TILE::SLOTS) * TILE::PLANE; zp.Pzh = ((z + 1) % TILE::SLOTS) * TILE::PLANE;
-    zp.Pa = ((z + 2) % TILE::SLOTS) * TILE::PLANE; zp.Pd = ((z - 2) % TILE::SLOTS) * TILE::PLANE;
+    zp.P0 = o[2];
+    zp.Pzl = o[1]; zp.Pzh = o[3];
+    zp.Pa = o[4]; zp.Pd = o[0];
     zp.Pb = zp.P0; zp.Pc = zp.P0;
     zp.sh = zp.sl = 0.5f;
     zp.qs = 0.25f * sigma2; zp.qz = zp.qs; zp.qzz = 0.5f * sigma2;
@@ -716,10 +807,13 @@ __device__ __forceinline__ ZPlanes z_planes_interior(int z, float sigma2)
     return zp;
 }
 
-template <class TILE>
-__device__ __forceinline__ ZPlanes z_planes(int z, int l, float sigma2)
+__device__ __forceinline__ ZPlanes z_planes(const int* o, int z, int l, float sigma2)
 {
-    auto plane = [&](int q) { return (clampi(q, 0, l - 1) % TILE::SLOTS) * TILE::PLANE; };
+    // a clamped plane is always one of the five resident ones
+    auto plane = [&](int q) {
+        const int k = clampi(q, 0, l - 1) - (z - 2);
+        return k <= 0 ? o[0] : (k == 1 ? o[1] : (k == 2 ? o[2] : (k == 3 ? o[3] : o[4])));
+    };
     const int zl = max(z - 1, 0), zh = min(z + 1, l - 1);
     const float sz = face_scale(z, l);
     ZPlanes zp;
@@ -729,6 +823,18 @@ __device__ __forceinline__ ZPlanes z_planes(int z, int l, float sigma2)
     zp.qs = 0.25f * sigma2; zp.qz = 0.5f * sz * sigma2; zp.qzz = sz * sigma2;
     zp.general = z < 2 || z > l - 3;
     return zp;
+}
+
+// A quad starts at x = 2 mod 4, so it is stored as two 8-byte-aligned pairs (two 2-byte-aligned code pairs).
+__device__ __forceinline__ void st_pair(float* dst, const float* v)
+{
+    *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+    *reinterpret_cast<float2*>(dst + 2) = make_float2(v[2], v[3]);
+}
+__device__ __forceinline__ void st_codes(uint8_t* dst, uint32_t c)
+{
+    *reinterpret_cast<uint16_t*>(dst) = (uint16_t)c;
+    *reinterpret_cast<uint16_t*>(dst + 2) = (uint16_t)(c >> 16);
 }
 
 // Second differences of four consecutive x voxels of one tile row (x and y interior), as two
@@ -813,66 +919,47 @@ __global__ void __launch_bounds__(HessTile::NT, HESS_MIN_CTAS)
 hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
 {
     using T = HessTile;
-    extern __shared__ __align__(16) float ring[];
+    extern __shared__ __align__(128) float ring[];
     const int tid = threadIdx.x;
     const int tx = tid & 31, ty = tid >> 5;
     int bid = blockIdx.x;
     const int bx = bid % p.ntx; bid /= p.ntx;
     const int by = bid % p.nty;
     const int bz = bid / p.nty;
-    const int x0 = bx * T::TX - 2, y0 = by * T::TY - 2;       // global coordinates of tile entry (0, 0)
+    // Tile bx covers the voxels x = 2 + TX * bx + [0, TX): the x faces 0, 1 belong to K3b anyway, and the box that
+    // holds x-2 .. x+2 of them then starts at x0 = TX * bx, a multiple of 4 floats -- the copy engine rejects an
+    // innermost coordinate that is not 16-byte aligned.  (y and z coordinates are free.)
+    const int x0 = bx * T::TX, y0 = by * T::TY - 2;           // global coordinates of tile entry (0, 0)
     const int w = p.f.w, h = p.f.h, l = p.f.l;
     // centre planes of this CTA (z faces included: see ZPlanes; x and y faces belong to K3b)
     const int zs = p.z_begin + bz * p.zchunk;
     const int ze = min(zs + p.zchunk, p.z_begin + p.nz);
     if (zs >= ze) return;
 
-    // staging map: the tile as 8-byte units (x0 is even, so every unit is 8-byte aligned in global memory);
-    // this thread's k-th unit, its shared-memory byte offset and global element offset, plane-independent.
-    // Units outside the volume are zero-filled: interior voxels never read them.
-    constexpr int UNITS = T::PLANE / 2, UPR = T::PW / 2;
-    constexpr int NU = (UNITS + T::NT - 1) / T::NT;           // 6 units per thread
-    int g_off[NU];
-    unsigned ok_mask = 0;
-#pragma unroll
-    for (int k = 0; k < NU; ++k) {
-        const int e = tid + k * T::NT;
-        const int r = e / UPR, c = 2 * (e - r * UPR);
-        const int gy = y0 + r, gx = x0 + c;
-        const bool ok = e < UNITS && gy >= 0 && gy < h && gx >= 0 && gx < w;
-        g_off[k] = ok ? gy * p.f.fpitch + gx : 0;
-        ok_mask |= (ok ? 1u : 0u) << k;
-    }
-    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
-    auto fetch = [&](int plane) {             // asynchronous global -> shared copy of one plane's tile
-        if (plane < 0 || plane > l - 1) return;   // beyond a z face: the face rules never read it
-        const float* __restrict__ src = p.f.F + (long long)(plane - p.f.base) * p.f.fplane;
-        const unsigned dst = ring_s + ((plane % T::SLOTS) * T::PLANE + 2 * tid) * 4;
-#pragma unroll
-        for (int k = 0; k < NU; ++k)
-            if (tid + k * T::NT < UNITS) {
-                const int nbytes = (ok_mask >> k) & 1u ? 8 : 0;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + k * T::NT * 8),
-                             "l"(src + g_off[k]), "r"(nbytes) : "memory");
-            }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
+    // plane tiles arrive by TMA (one instruction of thread 0 per plane), see TileRing
+    TileRing<T> tr;
+    tr.init(ring, reinterpret_cast<uint64_t*>(ring + T::SLOTS * T::SLOT), tid);
+    __syncthreads();
+    // prologue: planes zs-2 .. zs+2 on their way into the ring; the first four must have landed
+    if (tid == 0)
+        for (int q = zs - 2; q <= zs + 2; ++q) tr.issue(&p.tmap, x0, y0, q, p.f.base, l);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) tr.wait_next();
 
-    // prologue: planes zs-2 .. zs+2 on their way into the ring (all inside the volume)
-    for (int q = zs - 2; q <= zs + 2; ++q) fetch(q);
-
-    const int xq = bx * T::TX + 4 * tx;          // first of this thread's 4 x voxels
+    const int xq = bx * T::TX + 2 + 4 * tx;      // first of this thread's 4 x voxels (xq = 2 mod 4)
     bool m[4];                                   // voxel is interior in x
 #pragma unroll
-    for (int j = 0; j < 4; ++j) m[j] = xq + j >= 2 && xq + j <= w - 3;
+    for (int j = 0; j < 4; ++j) m[j] = xq + j <= w - 3;
     const bool any_x = m[0] || m[1] || m[2] || m[3];
     const bool all_x = m[0] && m[1] && m[2] && m[3] && p.vec_ok;
     float vmin = 3.4e38f, vmax = 0.0f;
 
-    for (int z = zs; z < ze; ++z) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                          // plane z+2 visible; everyone is done with plane z-3's slot
-        if (z + 1 < ze) fetch(z + 3);             // lands in that slot while plane z is processed
+    const long long plane_vox = (long long)h * w;
+    long long iz = (long long)(zs - p.z_begin) * plane_vox + xq;   // index of (xq, 0, z) in the own-plane outputs
+    for (int z = zs; z < ze; ++z, iz += plane_vox) {
+        __syncthreads();                          // everyone is done with plane z-3's slot
+        if (tid == 0 && z + 1 < ze) tr.issue(&p.tmap, x0, y0, z + 3, p.f.base, l);   // lands there while plane z is processed
+        tr.wait_next();                           // plane z+2 has landed
 
         const bool z_general = z < 2 || z > l - 3;
 
@@ -883,10 +970,10 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
             if (y < 2 || y > h - 3 || !any_x) continue;
             // second differences of the quad as two packed pairs (voxels 0,1 and 2,3)
             float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
-            if (z_general) quad_hessians<true>(ring, z_planes<T>(z, l, p.k.sigma2), (yl + 2) * T::PW + 4 * tx, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
-            else quad_hessians<false>(ring, z_planes_interior<T>(z, p.k.sigma2), (yl + 2) * T::PW + 4 * tx, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+            if (z_general) quad_hessians<true>(ring, z_planes(tr.o, z, l, p.k.sigma2), (yl + 2) * T::PW + 4 * tx, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+            else quad_hessians<false>(ring, z_planes_interior(tr.o, p.k.sigma2), (yl + 2) * T::PW + 4 * tx, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
 
-            const long long i0 = ((long long)(z - p.z_begin) * h + y) * w + xq;
+            const long long i0 = iz + (long long)y * w;
             if (MODE == 2 || !all_x) {            // stage dump; quads that straddle an x face; unaligned widths
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -907,7 +994,10 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
                 continue;
             }
             float jold[4] = { 0.f, 0.f, 0.f, 0.f };
-            if (MODE == 1) *reinterpret_cast<float4*>(jold) = *reinterpret_cast<const float4*>(p.J + i0);
+            if (MODE == 1) {
+                *reinterpret_cast<float2*>(jold) = *reinterpret_cast<const float2*>(p.J + i0);
+                *reinterpret_cast<float2*>(jold + 2) = *reinterpret_cast<const float2*>(p.J + i0 + 2);
+            }
             float jn[4];
             uint32_t cx = 0, cy = 0, cz = 0;      // four direction codes each, byte j = voxel j
             float ex[4], ey[4], ez[4];
@@ -930,18 +1020,12 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
                 vmin = fminf(vmin, fminf(jn[j], jn[j + 1])); vmax = fmaxf(vmax, fmaxf(jn[j], jn[j + 1]));
             }
             if (MODE == 0) {
-                *reinterpret_cast<float4*>(p.J + i0) = make_float4(jn[0], jn[1], jn[2], jn[3]);
-                *reinterpret_cast<uint32_t*>(p.Vx + i0) = cx;
-                *reinterpret_cast<uint32_t*>(p.Vy + i0) = cy;
-                *reinterpret_cast<uint32_t*>(p.Vz + i0) = cz;
-                if (p.scale_idx) *reinterpret_cast<uint32_t*>(p.scale_idx + i0) = 0u;
-                if (p.dir) {
-                    *reinterpret_cast<float4*>(p.dir + i0) = make_float4(ex[0], ex[1], ex[2], ex[3]);
-                    *reinterpret_cast<float4*>(p.dir + p.voxels + i0) = make_float4(ey[0], ey[1], ey[2], ey[3]);
-                    *reinterpret_cast<float4*>(p.dir + 2 * p.voxels + i0) = make_float4(ez[0], ez[1], ez[2], ez[3]);
-                }
+                st_pair(p.J + i0, jn);
+                st_codes(p.Vx + i0, cx); st_codes(p.Vy + i0, cy); st_codes(p.Vz + i0, cz);
+                if (p.scale_idx) st_codes(p.scale_idx + i0, 0u);
+                if (p.dir) { st_pair(p.dir + i0, ex); st_pair(p.dir + p.voxels + i0, ey); st_pair(p.dir + 2 * p.voxels + i0, ez); }
             } else if (wr[0] || wr[1] || wr[2] || wr[3]) {
-                *reinterpret_cast<float4*>(p.J + i0) = make_float4(jn[0], jn[1], jn[2], jn[3]);
+                st_pair(p.J + i0, jn);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (wr[j]) {
@@ -957,6 +1041,7 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
                     }
             }
         }
+        tr.rotate();
     }
     if (MODE == 2) return;
     // warp-shuffle reductions of min (first scale) and max (last scale), one atomic per warp
@@ -988,9 +1073,10 @@ struct HessTileC {                               // tile of the compacting kerne
     static constexpr int TX = 128, TY = 8, NT = 256;
     static constexpr int PW = HessTile::PW;      // same row pitch as HessTile (quad_hessians relies on it)
     static constexpr int PH = TY + 4;
-    static constexpr int PLANE = PW * PH;        // 1584 floats
+    static constexpr int PLANE = PW * PH;        // 1584 floats: the TMA box
+    static constexpr int SLOT = (PLANE * 4 + 127) / 128 * 32;   // 1600 floats
     static constexpr int SLOTS = 6;
-    static constexpr int SMEM_BYTES = SLOTS * PLANE * 4;   // 38016
+    static constexpr int RING_BYTES = SLOTS * SLOT * 4;    // 38400
 };
 struct HessQueue {
     static constexpr int PAIRS = 2;                                  // packed pairs per thread per drain (ILP)
@@ -1001,102 +1087,114 @@ struct HessQueue {
     // power of two so that the ring index is a mask.
     static constexpr int CAP = 2048;
     static_assert(CAP >= BATCH + APPEND, "queue too small");
-    static constexpr int BYTES = CAP * 32;                           // entry = 2 x float4: {Dxx,Dxy,Dxz,Dyy} {Dyz,Dzz,J,pos}
+    // Structure of arrays: field f of entry e sits at float f * CAP + e, fields = Dxx, Dxy, Dxz, Dyy, Dyz, Dzz, stored J,
+    // packed position.  Appends are eight predicated 32-bit stores; a drain reads entries (e, e + 1), e even, as one
+    // 64-bit load per field, which IS the packed register pair of the eigen stage.
+    static constexpr int FIELDS = 8;
+    static constexpr int BYTES = CAP * FIELDS * 4;
+    static constexpr int SMEM_BYTES = HessTileC::RING_BYTES + BYTES + HessTileC::SLOTS * 8 + 16;   // + mbarriers + tail counter
 };
+
+// eight predicated 32-bit shared stores of one queue entry (no branch, no register marshalling)
+__device__ __forceinline__ void queue_append(uint32_t addr, bool pred, float d0, float d1, float d2, float d3, float d4,
+                                             float d5, float jold, int pos)
+{
+    constexpr int S = HessQueue::CAP * 4;          // byte stride between the field arrays
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "@p st.shared.f32 [%0], %2;\n\t"
+        "@p st.shared.f32 [%0 + %10], %3;\n\t"
+        "@p st.shared.f32 [%0 + %11], %4;\n\t"
+        "@p st.shared.f32 [%0 + %12], %5;\n\t"
+        "@p st.shared.f32 [%0 + %13], %6;\n\t"
+        "@p st.shared.f32 [%0 + %14], %7;\n\t"
+        "@p st.shared.f32 [%0 + %15], %8;\n\t"
+        "@p st.shared.b32 [%0 + %16], %9;\n\t}"
+        ::"r"(addr), "r"((uint32_t)pred), "f"(d0), "f"(d1), "f"(d2), "f"(d3), "f"(d4), "f"(d5), "f"(jold), "r"(pos),
+          "n"(S), "n"(2 * S), "n"(3 * S), "n"(4 * S), "n"(5 * S), "n"(6 * S), "n"(7 * S) : "memory");
+}
 
 __global__ void __launch_bounds__(HessTileC::NT, 2)
 hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
 {
     using T = HessTileC;
     using Q = HessQueue;
-    extern __shared__ __align__(16) float ring[];
-    float4* q4 = reinterpret_cast<float4*>(ring + T::SLOTS * T::PLANE);   // CAP entries of 2 float4
-    __shared__ unsigned s_tail;                            // entries ever appended (the ring index is tail % CAP)
+    extern __shared__ __align__(128) float ring[];
+    float* qf = ring + T::SLOTS * T::SLOT;                                 // FIELDS arrays of CAP floats
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(qf + Q::FIELDS * Q::CAP);
+    unsigned* s_tail = reinterpret_cast<unsigned*>(mbar + T::SLOTS);       // entries ever appended (ring index = tail % CAP)
     const int tid = threadIdx.x;
     const int tx = tid & 31, ty = tid >> 5;
     int bid = blockIdx.x;
     const int bx = bid % p.ntx; bid /= p.ntx;
     const int by = bid % p.nty;
     const int bz = bid / p.nty;
-    const int x0 = bx * T::TX - 2, y0 = by * T::TY - 2;
+    const int x0 = bx * T::TX, y0 = by * T::TY - 2;           // tile bx covers x = 2 + TX * bx + [0, TX), see hessian_eigen_kernel
     const int w = p.f.w, h = p.f.h, l = p.f.l;
     const int zs = p.z_begin + bz * p.zchunk;
     const int ze = min(zs + p.zchunk, p.z_begin + p.nz);
     if (zs >= ze) return;
-    if (tid == 0) s_tail = 0;
+    if (tid == 0) *s_tail = 0;
 
-    constexpr int UNITS = T::PLANE / 2, UPR = T::PW / 2;
-    constexpr int NU = (UNITS + T::NT - 1) / T::NT;
-    int g_off[NU];
-    unsigned ok_mask = 0;
-#pragma unroll
-    for (int k = 0; k < NU; ++k) {
-        const int e = tid + k * T::NT;
-        const int r = e / UPR, c = 2 * (e - r * UPR);
-        const int gy = y0 + r, gx = x0 + c;
-        const bool ok = e < UNITS && gy >= 0 && gy < h && gx >= 0 && gx < w;
-        g_off[k] = ok ? gy * p.f.fpitch + gx : 0;
-        ok_mask |= (ok ? 1u : 0u) << k;
-    }
-    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
-    auto fetch = [&](int plane) {
-        if (plane < 0 || plane > l - 1) return;   // beyond a z face: the face rules never read it
-        const float* __restrict__ src = p.f.F + (long long)(plane - p.f.base) * p.f.fplane;
-        const unsigned dst = ring_s + ((plane % T::SLOTS) * T::PLANE + 2 * tid) * 4;
-#pragma unroll
-        for (int k = 0; k < NU; ++k)
-            if (tid + k * T::NT < UNITS) {
-                const int nbytes = (ok_mask >> k) & 1u ? 8 : 0;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + k * T::NT * 8),
-                             "l"(src + g_off[k]), "r"(nbytes) : "memory");
-            }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    for (int q = zs - 2; q <= zs + 2; ++q) fetch(q);
+    TileRing<T> tr;
+    tr.init(ring, mbar, tid);
+    __syncthreads();
+    if (tid == 0)
+        for (int q = zs - 2; q <= zs + 2; ++q) tr.issue(&p.tmap, x0, y0, q, p.f.base, l);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) tr.wait_next();
 
-    const int xq = bx * T::TX + 4 * tx;
+    const int xq = bx * T::TX + 2 + 4 * tx;
     bool m[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) m[j] = xq + j >= 2 && xq + j <= w - 3;
+    for (int j = 0; j < 4; ++j) m[j] = xq + j <= w - 3;
     const bool any_x = m[0] || m[1] || m[2] || m[3];
     const bool vec_j = p.vec_ok && xq + 3 < w;
     float vmax = 0.0f;
     unsigned head = 0;        // entries [head, tail) are pending; every thread carries the same value
     // The stored response of the thread's quad is fetched one plane ahead, so that the load is in
     // flight during a whole plane of work instead of stalling the append.
-    const int yrow = by * T::TY + ty;
+    const int yl = ty;                            // one tile row per warp
+    const int yrow = by * T::TY + yl;
     const bool row_ok = yrow >= 2 && yrow <= h - 3 && any_x;
+    const long long plane_vox = (long long)h * w;
+    const float* jp = p.J + ((long long)(zs - p.z_begin) * h + yrow) * w + xq;   // the quad's stored J at plane z (dereferenced only if row_ok)
     float jnext[4] = { 0.f, 0.f, 0.f, 0.f };
-    auto load_j = [&](int z) {
-        const long long i0 = ((long long)(z - p.z_begin) * h + yrow) * w + xq;
-        if (vec_j) *reinterpret_cast<float4*>(jnext) = __ldcs(reinterpret_cast<const float4*>(p.J + i0));
-        else
+    auto load_j = [&](const float* src) {
+        if (vec_j) {                              // xq = 2 mod 4: the quad is two aligned pairs
+            *reinterpret_cast<float2*>(jnext) = __ldcs(reinterpret_cast<const float2*>(src));
+            *reinterpret_cast<float2*>(jnext + 2) = __ldcs(reinterpret_cast<const float2*>(src + 2));
+        } else
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (m[j]) jnext[j] = p.J[i0 + j];
+            for (int j = 0; j < 4; ++j) if (m[j]) jnext[j] = src[j];
     };
-    if (row_ok) load_j(zs);
+    if (row_ok) load_j(jp);
+    const uint32_t q_s = smem_u32(qf);
+    const int o_quad = (yl + 2) * T::PW + 4 * tx;
+    int pos0 = (yl << 7) | (4 * tx);              // + (z - zs) << 10
 
-    // Phase B on entries [first, first + count) (ring positions): PAIRS independent packed pairs per thread
+    // Phase B on entries [first, first + count) (ring positions, first even): PAIRS independent packed pairs per thread
     auto drain = [&](unsigned first, int count) {
 #pragma unroll
         for (int q = 0; q < Q::PAIRS; ++q) {
             const int o = 2 * (tid + q * T::NT);           // entries o, o + 1 of the batch
             if (o >= count) continue;
             const bool two = o + 1 < count;
-            const int e0 = (int)((first + o) & (Q::CAP - 1));
-            const int e1 = two ? (int)((first + o + 1) & (Q::CAP - 1)) : e0;
-            const float4 a0 = q4[2 * e0], c0 = q4[2 * e0 + 1], a1 = q4[2 * e1], c1 = q4[2 * e1 + 1];
+            const float* e0 = qf + ((first + o) & (Q::CAP - 1));
+            float2 f[Q::FIELDS];
+#pragma unroll
+            for (int k = 0; k < Q::FIELDS; ++k) f[k] = *reinterpret_cast<const float2*>(e0 + k * Q::CAP);
             Eig3x2 e;
-            eig_sym3<float2, true>(make_float2(a0.x, a1.x), make_float2(a0.y, a1.y), make_float2(a0.z, a1.z),
-                                   make_float2(a0.w, a1.w), make_float2(c0.x, c1.x), make_float2(c0.y, c1.y), e);
+            eig_sym3<float2, true>(f[0], f[1], f[2], f[3], f[4], f[5], e);
             const float2 v = vesselness<float2, true>(e, p.k);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (k == 1 && !two) break;
                 const float vk = k ? v.y : v.x;
-                if (vk > (k ? c1.z : c0.z)) {
-                    const int pos = __float_as_int(k ? c1.w : c0.w);   // (z - zs) << 10 | row << 7 | column
-                    const int x = bx * T::TX + (pos & 127), y = by * T::TY + ((pos >> 7) & 7), z = zs + (pos >> 10);
+                if (vk > (k ? f[6].y : f[6].x)) {
+                    const int pos = __float_as_int(k ? f[7].y : f[7].x);   // (z - zs) << 10 | row << 7 | column
+                    const int x = bx * T::TX + 2 + (pos & 127), y = by * T::TY + ((pos >> 7) & 7), z = zs + (pos >> 10);
                     const long long i = ((long long)(z - p.z_begin) * h + y) * w + x;
                     p.J[i] = vk;
                     p.Vx[i] = (uint8_t)dir_code(k ? e.vx.y : e.vx.x);
@@ -1115,20 +1213,19 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     };
 
     for (int z = zs; z < ze; ++z) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                          // plane z+2 visible; nobody reads plane z-3's slot or drains any more
-        if (z + 1 < ze) fetch(z + 3);
+        __syncthreads();                          // nobody reads plane z-3's slot or drains any more
+        if (tid == 0 && z + 1 < ze) tr.issue(&p.tmap, x0, y0, z + 3, p.f.base, l);
+        tr.wait_next();                           // plane z+2 has landed
         const bool z_general = z < 2 || z > l - 3;
-        const int yl = ty;                        // one tile row per warp
-        const int y = by * T::TY + yl;
         // ---- phase A: second differences, the diagonal-sum test, append survivors ----
         bool surv[4] = { false, false, false, false };
         float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
         const float jold[4] = { jnext[0], jnext[1], jnext[2], jnext[3] };
-        if (row_ok && z + 1 < ze) load_j(z + 1);
+        jp += plane_vox;
+        if (row_ok && z + 1 < ze) load_j(jp);
         if (row_ok) {
-            if (z_general) quad_hessians<true>(ring, z_planes<T>(z, l, p.k.sigma2), (yl + 2) * T::PW + 4 * tx, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
-            else quad_hessians<false>(ring, z_planes_interior<T>(z, p.k.sigma2), (yl + 2) * T::PW + 4 * tx, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+            if (z_general) quad_hessians<true>(ring, z_planes(tr.o, z, l, p.k.sigma2), o_quad, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+            else quad_hessians<false>(ring, z_planes_interior(tr.o, p.k.sigma2), o_quad, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 const float2 sxy = vadd(Hxx[g], Hyy[g]), sxz = vadd(Hxx[g], Hzz[g]), syz = vadd(Hyy[g], Hzz[g]);
@@ -1140,24 +1237,24 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         const unsigned b2 = __ballot_sync(0xffffffffu, surv[2]), b3 = __ballot_sync(0xffffffffu, surv[3]);
         const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
         unsigned base = 0;
-        if (tx == 0 && n0 + n1 + n2 + n3 > 0) base = atomicAdd(&s_tail, (unsigned)(n0 + n1 + n2 + n3));
+        if (tx == 0 && n0 + n1 + n2 + n3 > 0) base = atomicAdd(s_tail, (unsigned)(n0 + n1 + n2 + n3));
         base = __shfl_sync(0xffffffffu, base, 0);
         const unsigned below = (1u << tx) - 1u;
         const unsigned slot[4] = { base + __popc(b0 & below), base + n0 + __popc(b1 & below),
                                    base + n0 + n1 + __popc(b2 & below), base + n0 + n1 + n2 + __popc(b3 & below) };
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (surv[j]) {
-                typedef Lanes<float2> L2;
-                const int e = (int)(slot[j] & (Q::CAP - 1));
-                q4[2 * e] = make_float4(L2::get(Hxx[j >> 1], j & 1), L2::get(Hxy[j >> 1], j & 1),
-                                        L2::get(Hxz[j >> 1], j & 1), L2::get(Hyy[j >> 1], j & 1));
-                q4[2 * e + 1] = make_float4(L2::get(Hyz[j >> 1], j & 1), L2::get(Hzz[j >> 1], j & 1), jold[j],
-                                            __int_as_float(((z - zs) << 10) | (yl << 7) | (4 * tx + j)));
-            }
+        for (int j = 0; j < 4; ++j) {
+            typedef Lanes<float2> L2;
+            queue_append(q_s + 4 * (slot[j] & (Q::CAP - 1)), surv[j],
+                         L2::get(Hxx[j >> 1], j & 1), L2::get(Hxy[j >> 1], j & 1), L2::get(Hxz[j >> 1], j & 1),
+                         L2::get(Hyy[j >> 1], j & 1), L2::get(Hyz[j >> 1], j & 1), L2::get(Hzz[j >> 1], j & 1),
+                         jold[j], pos0 + j);
+        }
+        pos0 += 1 << 10;
+        tr.rotate();
         __syncthreads();                          // appended entries and the tail are visible
         // ---- phase B: full batches from the head of the queue (everything after the last plane) ----
-        const unsigned tail = s_tail;
+        const unsigned tail = *reinterpret_cast<volatile unsigned*>(s_tail);
         const bool flush = z + 1 == ze;
         while (tail - head >= (unsigned)Q::BATCH || (flush && tail != head)) {
             const int take = (int)min(tail - head, (unsigned)Q::BATCH);
