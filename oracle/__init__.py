@@ -178,6 +178,13 @@ class Reference:
         L.ref_extract_seeds.restype = C.c_long
         L.ref_extract_seeds.argtypes = [C.c_double, _u8p, C.c_int, C.c_int, C.c_int,
                                         _u8p, _u8p, _u8p, _f32p, C.c_long]
+        self.has_trace = hasattr(L, "ref_trace")
+        if self.has_trace:
+            L.ref_trace.restype = C.c_int
+            L.ref_trace.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _u8p, _u8p, _f32p, C.c_int,
+                                    C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                    C.c_int, _f32p, C.c_long, _f32p, C.c_long, C.POINTER(C.c_int), C.c_long,
+                                    C.POINTER(C.c_long)]
 
     @staticmethod
     def available() -> bool:
@@ -224,3 +231,26 @@ class Reference:
         if n < 0 or n > cap:
             raise RuntimeError(f"ref_extract_seeds returned {n} (cap {cap})")
         return out[:n].copy()
+
+    def trace(self, I, J8, Vx, Vy, Vz, sigmas, tolerance=5.0, znccth=0.3, kappa=3.0, step=2, ni=200, np_=20,
+              zdist=2.0, nodepervol=4, max_traces=5000):
+        """The plugin's pipeline downstream of Frangi (seeds -> correlation filter -> SMC traces), README usage
+        `-p 2,4,6 0 5 0.3 3 2 200 20 2 4 1`.  Returns dict(seeds [n,8], nodes [m,10], nbr int[], counts)."""
+        I, w, h, l = _check_vol(I)
+        J8, Vx, Vy, Vz = (np.ascontiguousarray(v, np.uint8) for v in (J8, Vx, Vy, Vz))
+        s = np.ascontiguousarray(sigmas, np.float32)
+        scap = max(1024, I.size // 8)
+        ncap = max(1 << 16, I.size // 4)
+        seeds = np.empty((scap, 8), np.float32)
+        nodes = np.empty((ncap, 10), np.float32)
+        nbr = np.empty(4 * ncap, np.int32)
+        counts = (C.c_long * 5)()
+        rc = self.lib.ref_trace(_p(I, _u8p), w, h, l, _p(J8, _u8p), _p(Vx, _u8p), _p(Vy, _u8p), _p(Vz, _u8p),
+                                _p(s, _f32p), len(s), tolerance, znccth, kappa, step, ni, np_, zdist, nodepervol,
+                                max_traces, _p(seeds, _f32p), scap, _p(nodes, _f32p), ncap,
+                                nbr.ctypes.data_as(C.POINTER(C.c_int)), nbr.size, counts)
+        c = [int(v) for v in counts]
+        if rc != 0 or c[1] > scap or c[2] > ncap or c[3] > nbr.size:
+            raise RuntimeError(f"ref_trace rc={rc} counts={c}")
+        return dict(seeds=seeds[:c[1]].copy(), nodes=nodes[:c[2]].copy(), nbr=nbr[:c[3]].copy(),
+                    n_extracted=c[0], n_traces=c[4])

@@ -13,11 +13,28 @@
 //   Frangi::eigen_decomposition_static(A,V,d)    frangi.h:54,  frangi.cpp:1230
 //   Frangi::frangi3d(...)                        frangi.h:33,  frangi.cpp:152
 //   SeedExtractor::extractSeeds(...)             seed.h:101,   seed.cpp:556
+//   Tracker::Tracker / znccBBB / trackPos / trackNeg   tracker.h:144,182,171,173  (ref_trace, config 5)
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <ctime>
 #include <iostream>
 #include <vector>
 
 #include "frangi.h"
+#include "node.h"
 #include "seed.h"
+#include "tracker.h"
+
+// The tracker reseeds the C generator with srand(time(NULL)) on every resampling step
+// (tracker.cpp:655,808,1003,1098).  For a reproducible trace the library carries its own time():
+// it is linked with -Bsymbolic-functions, so the reference objects inside this .so bind to it and
+// every run (and both arms of the end-to-end comparison) draws the same numbers.
+extern "C" time_t time(time_t* t) noexcept
+{
+    if (t) *t = (time_t)1;
+    return (time_t)1;
+}
 
 namespace {
 // The reference prints progress to std::cout from every stage; park the stream
@@ -92,6 +109,94 @@ long ref_extract_seeds(double tolerance, unsigned char* J8, int w, int h, int l,
         out[6 * i + 3] = seeds[i].vx; out[6 * i + 4] = seeds[i].vy; out[6 * i + 5] = seeds[i].vz;
     }
     return n;
+}
+
+
+// Everything the plugin does downstream of the Frangi filter up to the raw node list, restated from the
+// one call site (Advantra_plugin.cpp) around the UNMODIFIED reference classes:
+//   :2416-2419  node list with the dummy node 0            :2484  smap = 0 (somaradius == 0)
+//   :2525-2526  SeedExtractor / Tracker construction        :2549  extractSeeds
+//   :2560-2573  soma / correlation filter (Tracker::znccBBB, seeds below znccth dropped, walking backwards)
+//   :2577-2586  sort by correlation, highest first (CompareSeedCorr :347-352)
+//   :2602-2650  neighbour offsets: vol == 1 only here (ioff[i] = 0, the README usage `... 4 1`)
+//   :2657-2719  trace loop: trackPos + trackNeg from every seed whose voxel holds < nodepervol nodes
+// Plugin constants Kc = 20, neff_ratio = 0.8 (:63-64), MAX_TRACE_COUNT = 5000 (:72).
+// Inputs are the image and the Frangi outputs (J8, Vx, Vy, Vz) of EITHER arm; the post-processing of
+// reconstruct() is not run (it writes no final SWC with default settings), the comparison is
+// on the node list n0.  Outputs: seeds_out rows (x, y, z, vx, vy, vz, score, corr) after filter + sort;
+// nodes_out rows (x, y, z, vx, vy, vz, corr, sig, type, number of neighbours); nbr_out = the neighbour
+// indices of all nodes, concatenated.  counts = {seeds extracted, seeds kept, nodes, neighbour entries, traces}.
+__attribute__((visibility("default")))
+int ref_trace(unsigned char* img, int w, int h, int l, unsigned char* J8, unsigned char* Vx, unsigned char* Vy,
+              unsigned char* Vz, const float* sigmas, int nsig, float tolerance, float znccth, float kappa, int step,
+              int ni, int np, float zdist, int nodepervol, int max_traces, float* seeds_out, long seeds_cap,
+              float* nodes_out, long nodes_cap, int* nbr_out, long nbr_cap, long* counts)
+{
+    QuietCout q;
+    FILE* saved_stdout = stdout;                 // the tracker also chats through printf
+    FILE* devnull = fopen("/dev/null", "w");
+    if (devnull) stdout = devnull;
+    const float Kc = 20.0f, neff_ratio = 0.8f;
+    const int vol = 1;
+    const long size = (long)w * h * l;
+    std::vector<float> sigs(sigmas, sigmas + nsig);
+    std::vector<Node> n0;
+    Node n00;
+    n0.push_back(n00);
+    std::vector<int> smap(size, 0);
+    Tracker t(sigs, step, np, ni, kappa, l == 1, znccth, Kc, neff_ratio, zdist, nodepervol);
+    std::vector<seed> seeds_init;
+    SeedExtractor::extractSeeds(tolerance, J8, w, h, l, Vx, Vy, Vz, seeds_init);
+    counts[0] = (long)seeds_init.size();
+    float dummy_sig;
+    for (long i = (long)seeds_init.size() - 1; i >= 0; --i) {
+        const long j = (long)((int)round(seeds_init[i].z)) * w * h + (int)round(seeds_init[i].y) * w + (int)round(seeds_init[i].x);
+        if (smap[j] > 0) seeds_init.erase(seeds_init.begin() + i);
+        else {
+            seeds_init[i].corr = t.znccBBB(seeds_init[i].x, seeds_init[i].y, seeds_init[i].z, seeds_init[i].vx,
+                                           seeds_init[i].vy, seeds_init[i].vz, img, w, h, l, dummy_sig);
+            if (seeds_init[i].corr < znccth) seeds_init.erase(seeds_init.begin() + i);
+        }
+    }
+    std::vector<long> si(seeds_init.size());
+    for (size_t i = 0; i < si.size(); ++i) si[i] = (long)i;
+    std::sort(si.begin(), si.end(), [&](const int& a, const int& b) { return seeds_init[a].corr > seeds_init[b].corr; });
+    std::vector<seed> seeds;
+    for (size_t i = 0; i < si.size(); ++i) seeds.push_back(seeds_init[si[i]]);
+    counts[1] = (long)seeds.size();
+    for (long i = 0; i < (long)seeds.size() && i < seeds_cap; ++i) {
+        float* r = seeds_out + 8 * i;
+        r[0] = seeds[i].x; r[1] = seeds[i].y; r[2] = seeds[i].z; r[3] = seeds[i].vx; r[4] = seeds[i].vy; r[5] = seeds[i].vz;
+        r[6] = seeds[i].score; r[7] = seeds[i].corr;
+    }
+    std::vector<long*> ioff(size, (long*)0);     // vol == 1: no neighbouring voxels
+    std::vector<unsigned char> npervol_map(size, 0);
+    std::vector<int> nidx_map(size, 0);
+    long trace_count = 0;
+    for (long i = 0; i < (long)seeds.size(); ++i) {
+        const long sidx = (long)((int)round(seeds[i].z)) * w * h + (int)round(seeds[i].y) * w + (int)round(seeds[i].x);
+        if ((int)npervol_map[sidx] < nodepervol) {
+            trace_count++;
+            t.trackPos(seeds[i], img, n0, w, h, l, smap.data(), npervol_map.data(), vol, ioff.data(), nidx_map.data());
+            t.trackNeg(seeds[i], img, n0, w, h, l, smap.data(), npervol_map.data(), vol, ioff.data(), nidx_map.data());
+            if (trace_count > max_traces) break;
+        }
+    }
+    counts[2] = (long)n0.size();
+    counts[4] = trace_count;
+    long nn = 0;
+    for (long i = 0; i < (long)n0.size(); ++i) {
+        if (i < nodes_cap) {
+            float* r = nodes_out + 10 * i;
+            r[0] = n0[i].x; r[1] = n0[i].y; r[2] = n0[i].z; r[3] = n0[i].vx; r[4] = n0[i].vy; r[5] = n0[i].vz;
+            r[6] = n0[i].corr; r[7] = n0[i].sig; r[8] = (float)n0[i].type; r[9] = (float)n0[i].nbr.size();
+        }
+        for (size_t k = 0; k < n0[i].nbr.size(); ++k, ++nn)
+            if (nn < nbr_cap) nbr_out[nn] = n0[i].nbr[k];
+    }
+    counts[3] = nn;
+    if (devnull) { fflush(devnull); stdout = saved_stdout; fclose(devnull); }
+    return 0;
 }
 
 }  // extern "C"
