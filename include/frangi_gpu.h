@@ -152,6 +152,23 @@ int frangi_gpu_vesselness_stage(const float* Dxx, const float* Dxy, const float*
                                 float* v_out, float* dir_out, float* lambda_out, int device,
                                 unsigned stage_flags);
 
+/* ---- f3: the data-parallel pre-pass of the first consumer -----------------------
+ * Replaces the per-layer scans at the head of SeedExtractor::extractSeeds (seed.h:101,
+ * seed.cpp:574-632): for every z layer of the 8-bit vesselness the layer range
+ * (globalMin / globalMax, :578-586), the 8-neighbour candidate maxima (:590-614) and their
+ * ranking keys `(int)((v-globalMin)*vFactor) << 32 | y*w+x` sorted ascending (:616-630) --
+ * bit for bit the reference's maxPoints arrays, all layers concatenated (layer z starts at
+ * sum(n_max[0..z-1])).  The sequential flood-fill analysis (:643-782) stays with the caller.
+ * frangi_gpu_seed_candidates works on the J8 volume the last run left on the device(s)
+ * (every slab handles its own layers; layer arrays hold the handle's local planes);
+ * the _host variant takes any uint8 volume.  keys may be NULL (count only); on return
+ * *n_keys is the number of candidates, an error is raised if it exceeds keys_cap. */
+int frangi_gpu_seed_candidates(frangi_gpu_t* h, uint8_t* layer_min, uint8_t* layer_max, int* n_max,
+                               int64_t* keys, int64_t keys_cap, int64_t* n_keys);
+int frangi_gpu_seed_candidates_host(const uint8_t* J8_host, int w, int h, int l, uint8_t* layer_min,
+                                    uint8_t* layer_max, int* n_max, int64_t* keys, int64_t keys_cap,
+                                    int64_t* n_keys, int device);
+
 /* ---- utilities --------------------------------------------------------------*/
 void* frangi_gpu_host_alloc(size_t bytes); /* pinned host memory (NULL on failure) */
 void frangi_gpu_host_free(void* p);

@@ -79,6 +79,9 @@ class Oracle:
         L.oracle_extract_seeds.restype = C.c_long
         L.oracle_extract_seeds.argtypes = [C.c_double, _u8p, C.c_int, C.c_int, C.c_int,
                                            _u8p, _u8p, _u8p, _f32p, C.c_long]
+        L.oracle_seed_candidates.restype = C.c_long
+        L.oracle_seed_candidates.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, C.POINTER(C.c_int),
+                                             C.POINTER(C.c_int64), C.c_long]
 
     def gauss_taps(self, sigma: float):
         r = self.lib.oracle_gauss_radius(sigma)
@@ -155,6 +158,20 @@ class Oracle:
         if n < 0 or n > cap:
             raise RuntimeError(f"oracle_extract_seeds returned {n} (cap {cap})")
         return out[:n].copy()
+
+
+    def seed_candidates(self, J8):
+        """The pre-pass of extractSeeds (seed.cpp:574-632): per-layer range, candidate counts, ranked keys."""
+        J8, w, h, l = _check_vol(J8)
+        lo = np.empty(l, np.uint8); hi = np.empty(l, np.uint8); n = np.empty(l, np.int32)
+        cap = J8.size
+        keys = np.empty(cap, np.int64)
+        tot = self.lib.oracle_seed_candidates(_p(J8, _u8p), w, h, l, _p(lo, _u8p), _p(hi, _u8p),
+                                              n.ctypes.data_as(C.POINTER(C.c_int)),
+                                              keys.ctypes.data_as(C.POINTER(C.c_int64)), cap)
+        if tot < 0 or tot > cap:
+            raise RuntimeError(f"oracle_seed_candidates returned {tot}")
+        return dict(layer_min=lo, layer_max=hi, n_max=n, keys=keys[:tot].copy())
 
 
 class Reference:

@@ -50,6 +50,74 @@ static int cmp_i64(const void *a, const void *b)
     return (x > y) - (x < y);
 }
 
+/* The per-layer pre-pass of extractSeeds (seed.cpp:574-632): layer range, 8-neighbour candidate maxima
+ * (flags[p] = F_MAXIMUM), and the candidates ranked by height -- value in the upper 32 bits, pixel offset in
+ * the lower, sorted ascending.  flags must be zeroed by the caller.  Returns the number of candidates. */
+static int layer_candidates(const uint8_t *layer, int w, int h, uint8_t *flags, int64_t *ranked, float *lo_out,
+                            float *hi_out)
+{
+    const int64_t plane = (int64_t)w * h;
+    /* layer range, seed.cpp:578-586 */
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    for (int64_t p = 0; p < plane; ++p) {
+        float v = (float)(int)layer[p];
+        if (lo > v) lo = v;
+        if (hi < v) hi = v;
+    }
+    /* candidate maxima, seed.cpp:590-614 */
+    int n_max = 0;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float v = layer[(int64_t)y * w + x];
+            if (v == lo) continue;
+            if (on_border(x, y, w, h)) continue;
+            int is_max = 1;
+            for (int d = 0; d < 8; ++d) {
+                float vn = layer[(int64_t)(y + NBR_DY[d]) * w + (x + NBR_DX[d])];
+                if (vn > v) { is_max = 0; break; }
+            }
+            if (is_max) { flags[(int64_t)y * w + x] = F_MAXIMUM; ++n_max; }
+        }
+    /* rank by height: value in the upper 32 bits, pixel offset below, seed.cpp:616-632 */
+    float to_int = (float)(2e9 / (hi - lo));
+    int k = 0;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int p = x + y * w;
+            if (flags[p] == F_MAXIMUM) {
+                float fv = layer[p];
+                int iv = (int)((fv - lo) * to_int);
+                ranked[k++] = ((int64_t)iv << 32) | (int64_t)p;
+            }
+        }
+    qsort(ranked, (size_t)n_max, sizeof(int64_t), cmp_i64);
+    *lo_out = lo; *hi_out = hi;
+    return n_max;
+}
+
+/* The pre-pass alone, for the parity test of frangi_gpu_seed_candidates: per layer the range, the number of
+ * candidates and their ranked keys (all layers concatenated).  Returns the total number of keys (at most `cap`
+ * are written), -1 on allocation failure. */
+ORACLE_API long oracle_seed_candidates(const uint8_t *J8, int w, int h, int l, uint8_t *layer_min, uint8_t *layer_max,
+                                       int *n_max_out, int64_t *keys, long cap)
+{
+    const int64_t plane = (int64_t)w * h;
+    uint8_t *flags = (uint8_t *)malloc((size_t)plane);
+    int64_t *ranked = (int64_t *)malloc(sizeof(int64_t) * (size_t)plane);
+    long total = 0;
+    if (!flags || !ranked) { free(flags); free(ranked); return -1; }
+    for (int z = 0; z < l; ++z) {
+        float lo, hi;
+        memset(flags, 0, (size_t)plane);
+        int n = layer_candidates(J8 + (int64_t)z * plane, w, h, flags, ranked, &lo, &hi);
+        layer_min[z] = (uint8_t)lo; layer_max[z] = (uint8_t)hi; n_max_out[z] = n;
+        for (int k = 0; k < n; ++k, ++total)
+            if (total < cap) keys[total] = ranked[k];
+    }
+    free(flags); free(ranked);
+    return total;
+}
+
 /* Returns the number of seeds; writes at most `cap` rows (x,y,z,vx,vy,vz). */
 ORACLE_API long oracle_extract_seeds(double tolerance, const uint8_t *J8, int w, int h, int l,
                                      const uint8_t *Vx, const uint8_t *Vy, const uint8_t *Vz,
@@ -65,43 +133,8 @@ ORACLE_API long oracle_extract_seeds(double tolerance, const uint8_t *J8, int w,
     for (int z = 0; z < l; ++z) {
         const uint8_t *layer = J8 + (int64_t)z * plane;
         memset(flags, 0, (size_t)plane);
-
-        /* layer range, seed.cpp:578-586 */
-        float lo = FLT_MAX, hi = -FLT_MAX;
-        for (int64_t p = 0; p < plane; ++p) {
-            float v = (float)(int)layer[p];
-            if (lo > v) lo = v;
-            if (hi < v) hi = v;
-        }
-
-        /* candidate maxima, seed.cpp:590-614 */
-        int n_max = 0;
-        for (int y = 0; y < h; ++y)
-            for (int x = 0; x < w; ++x) {
-                float v = layer[(int64_t)y * w + x];
-                if (v == lo) continue;
-                if (on_border(x, y, w, h)) continue;
-                int is_max = 1;
-                for (int d = 0; d < 8; ++d) {
-                    float vn = layer[(int64_t)(y + NBR_DY[d]) * w + (x + NBR_DX[d])];
-                    if (vn > v) { is_max = 0; break; }
-                }
-                if (is_max) { flags[(int64_t)y * w + x] = F_MAXIMUM; ++n_max; }
-            }
-
-        /* rank by height: value in the upper 32 bits, pixel offset below, seed.cpp:616-632 */
-        float to_int = (float)(2e9 / (hi - lo));
-        int k = 0;
-        for (int y = 0; y < h; ++y)
-            for (int x = 0; x < w; ++x) {
-                int p = x + y * w;
-                if (flags[p] == F_MAXIMUM) {
-                    float fv = layer[p];
-                    int iv = (int)((fv - lo) * to_int);
-                    ranked[k++] = ((int64_t)iv << 32) | (int64_t)p;
-                }
-            }
-        qsort(ranked, (size_t)n_max, sizeof(int64_t), cmp_i64);
+        float lo, hi;
+        int n_max = layer_candidates(layer, w, h, flags, ranked, &lo, &hi);
 
         /* analyse from the highest maximum down, seed.cpp:643-782 */
         for (int im = n_max - 1; im >= 0; --im) {

@@ -22,7 +22,10 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_segmented_radix_sort.cuh>
+
 #include "frangi_kernels.cuh"
+#include "seed_kernels.cuh"
 #include "nccl_dyn.h"
 
 #define FRANGI_API extern "C" __attribute__((visibility("default")))
@@ -1330,4 +1333,110 @@ FRANGI_API int frangi_gpu_vesselness_stage(const float* Dxx, const float* Dxy, c
     for (int k = 0; k < 6; ++k) cudaFree(d[k]);
     cudaFree(dv); cudaFree(ddir); cudaFree(dlam);
     return rc;
+}
+
+// ---- f3: pre-pass of SeedExtractor::extractSeeds on the device (seed_kernels.cuh) ------------------
+namespace {
+
+// The pre-pass on `nl` layers of a dense device J8 volume; host outputs (layer_min/max/n_max per layer,
+// keys appended at keys[*n_keys ...]).  keys == NULL or a too small keys_cap only counts.
+int seed_candidates_device(const uint8_t* dJ8, int w, int h, int nl, cudaStream_t st, uint8_t* layer_min,
+                           uint8_t* layer_max, int* n_max, int64_t* keys, int64_t keys_cap, int64_t* n_keys)
+{
+    if (nl < 1) return 0;
+    if (nl > 65535) return fail(FRANGI_GPU_EINVAL, "seed_candidates: more than 65535 layers on one device");
+    const long long plane = (long long)w * h;
+    int *d_minmax = nullptr, *d_count = nullptr;
+    long long *d_off = nullptr, *d_in = nullptr, *d_out = nullptr;
+    void* d_tmp = nullptr;
+    auto cleanup = [&]() { cudaFree(d_minmax); cudaFree(d_count); cudaFree(d_off); cudaFree(d_in); cudaFree(d_out); cudaFree(d_tmp); };
+#define CKS(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return fail(FRANGI_GPU_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+    std::vector<int> h_minmax(2 * (size_t)nl), h_count(nl);
+    for (int z = 0; z < nl; ++z) { h_minmax[2 * z] = 255; h_minmax[2 * z + 1] = 0; }
+    CKS(cudaMalloc(&d_minmax, sizeof(int) * 2 * nl));
+    CKS(cudaMalloc(&d_count, sizeof(int) * nl));
+    CKS(cudaMalloc(&d_off, sizeof(long long) * (nl + 1)));
+    CKS(cudaMemcpyAsync(d_minmax, h_minmax.data(), sizeof(int) * 2 * nl, cudaMemcpyHostToDevice, st));
+    CKS(cudaMemsetAsync(d_count, 0, sizeof(int) * nl, st));
+    const int nb = (int)std::min<long long>(std::max<long long>(1, plane / (4 * 256 * 8)), 148 * 8);
+    j8_layer_minmax_kernel<<<dim3(nb, nl), 256, 0, st>>>(dJ8, plane, d_minmax);
+    g_launches++;
+    const dim3 grid((w + 31) / 32, (h + 7) / 8, nl), block(32, 8);
+    if (grid.y > 65535) { cleanup(); return fail(FRANGI_GPU_EINVAL, "seed_candidates: layer too tall"); }
+    j8_local_maxima_kernel<false><<<grid, block, 0, st>>>(dJ8, w, h, d_minmax, d_count, nullptr, nullptr);
+    g_launches++;
+    CKS(cudaGetLastError());
+    CKS(cudaMemcpyAsync(h_count.data(), d_count, sizeof(int) * nl, cudaMemcpyDeviceToHost, st));
+    CKS(cudaMemcpyAsync(h_minmax.data(), d_minmax, sizeof(int) * 2 * nl, cudaMemcpyDeviceToHost, st));
+    CKS(cudaStreamSynchronize(st));
+    std::vector<long long> h_off(nl + 1, 0);
+    for (int z = 0; z < nl; ++z) {
+        h_off[z + 1] = h_off[z] + h_count[z];
+        layer_min[z] = (uint8_t)h_minmax[2 * z]; layer_max[z] = (uint8_t)h_minmax[2 * z + 1];
+        n_max[z] = h_count[z];
+    }
+    const long long total = h_off[nl];
+    const int64_t at = *n_keys;
+    *n_keys = at + total;
+    if (!keys || at + total > keys_cap || total == 0) { cleanup(); return 0; }   // counted only (the caller checks n_keys against its capacity)
+    CKS(cudaMalloc(&d_in, sizeof(long long) * total));
+    CKS(cudaMalloc(&d_out, sizeof(long long) * total));
+    CKS(cudaMemcpyAsync(d_off, h_off.data(), sizeof(long long) * (nl + 1), cudaMemcpyHostToDevice, st));
+    CKS(cudaMemsetAsync(d_count, 0, sizeof(int) * nl, st));
+    j8_local_maxima_kernel<true><<<grid, block, 0, st>>>(dJ8, w, h, d_minmax, d_count, d_off, d_in);
+    g_launches++;
+    CKS(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CKS(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, d_in, d_out, total, nl, d_off, d_off + 1, 0, 63, st));
+    CKS(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    CKS(cub::DeviceSegmentedRadixSort::SortKeys(d_tmp, tmp_bytes, d_in, d_out, total, nl, d_off, d_off + 1, 0, 63, st));
+    g_launches++;
+    CKS(cudaMemcpyAsync(keys + at, d_out, sizeof(long long) * total, cudaMemcpyDeviceToHost, st));
+    CKS(cudaStreamSynchronize(st));
+#undef CKS
+    cleanup();
+    return 0;
+}
+
+}  // namespace
+
+FRANGI_API int frangi_gpu_seed_candidates(frangi_gpu_t* H, uint8_t* layer_min, uint8_t* layer_max, int* n_max, int64_t* keys,
+                                          int64_t keys_cap, int64_t* n_keys)
+{
+    if (!H || !layer_min || !layer_max || !n_max || !n_keys) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    if (!H->ran) return fail(FRANGI_GPU_ESTATE, "nothing has been run on this handle");
+    *n_keys = 0;
+    int zoff = 0;
+    for (auto& s : H->slabs) {       // layers are independent: every slab handles its own, in z order
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.s_main));
+        RC(seed_candidates_device(s.dJ8, H->w, H->h, s.ze - s.zb, s.s_main, layer_min + zoff, layer_max + zoff, n_max + zoff,
+                                  keys, keys_cap, n_keys));
+        zoff += s.ze - s.zb;
+    }
+    if (keys && *n_keys > keys_cap) return fail(FRANGI_GPU_EINVAL, "seed_candidates: %lld keys, capacity %lld", (long long)*n_keys, (long long)keys_cap);
+    return 0;
+}
+
+FRANGI_API int frangi_gpu_seed_candidates_host(const uint8_t* J8_host, int w, int h, int l, uint8_t* layer_min, uint8_t* layer_max,
+                                               int* n_max, int64_t* keys, int64_t keys_cap, int64_t* n_keys, int device)
+{
+    if (!J8_host || !layer_min || !layer_max || !n_max || !n_keys) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    if (w < 1 || h < 1 || l < 1 || (long long)w * h > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "bad volume %d x %d x %d", w, h, l);
+    RC(check_device(device));
+    CK(cudaSetDevice(device));
+    const size_t n = (size_t)w * h * l;
+    uint8_t* d = nullptr;
+    CK(cudaMalloc(&d, n));
+    cudaError_t e = cudaMemcpy(d, J8_host, n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return fail(FRANGI_GPU_ECUDA, "upload failed: %s", cudaGetErrorString(e)); }
+    *n_keys = 0;
+    int rc = 0;
+    for (int z0 = 0; z0 < l && rc == 0; z0 += 65535)
+        rc = seed_candidates_device(d + (size_t)z0 * w * h, w, h, std::min(65535, l - z0), 0, layer_min + z0, layer_max + z0, n_max + z0,
+                                    keys, keys_cap, n_keys);
+    cudaFree(d);
+    if (rc) return rc;
+    if (keys && *n_keys > keys_cap) return fail(FRANGI_GPU_EINVAL, "seed_candidates: %lld keys, capacity %lld", (long long)*n_keys, (long long)keys_cap);
+    return 0;
 }

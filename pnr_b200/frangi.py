@@ -67,6 +67,9 @@ SYMBOLS = {
                                        _VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_uint]),
     "frangi_gpu_vesselness_stage": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_float, C.c_float,
                                               C.c_float, C.c_int, _VP, _VP, _VP, C.c_int, C.c_uint]),
+    "frangi_gpu_seed_candidates": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int64, C.POINTER(C.c_int64)]),
+    "frangi_gpu_seed_candidates_host": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_int64,
+                                                  C.POINTER(C.c_int64), C.c_int]),
     "frangi_gpu_host_alloc": (_VP, [C.c_size_t]),
     "frangi_gpu_host_free": (None, [_VP]),
     "frangi_gpu_device_count": (C.c_int, []),
@@ -267,6 +270,20 @@ class FrangiPlan:
         return o
 
 
+    def seed_candidates(self, cap=None):
+        """Pre-pass of SeedExtractor::extractSeeds (seed.cpp:574-632) on the J8 volume the last run left on the
+        device: dict(layer_min u8[l], layer_max u8[l], n_max i32[l], keys i64[sum n_max]) (sorted per layer)."""
+        l = self.l
+        lo = np.empty(l, np.uint8); hi = np.empty(l, np.uint8); n = np.empty(l, np.int32)
+        total = C.c_int64(0)
+        if cap is None:   # count first
+            _check(self.lib.frangi_gpu_seed_candidates(self.handle, _ptr(lo), _ptr(hi), _ptr(n), None, 0, C.byref(total)))
+            cap = max(1, total.value)
+        keys = np.empty(cap, np.int64)
+        _check(self.lib.frangi_gpu_seed_candidates(self.handle, _ptr(lo), _ptr(hi), _ptr(n), _ptr(keys), cap, C.byref(total)))
+        return dict(layer_min=lo, layer_max=hi, n_max=n, keys=keys[:total.value].copy())
+
+
 class Frangi:
     """Same constructor, public fields and hot method as the reference class
     (frangi.h:5-59); frangi3d runs on the GPU(s)."""
@@ -339,3 +356,16 @@ class Frangi:
         if self._plan is not None:
             self._plan.close()
             self._plan = None
+
+
+def seed_candidates(J8, device=0):
+    """The same pre-pass on any uint8 volume [l][h][w] held by the host."""
+    J8, w, h, l = _vol(J8)
+    lib = load_library()
+    lo = np.empty(l, np.uint8); hi = np.empty(l, np.uint8); n = np.empty(l, np.int32)
+    total = C.c_int64(0)
+    _check(lib.frangi_gpu_seed_candidates_host(_ptr(J8), w, h, l, _ptr(lo), _ptr(hi), _ptr(n), None, 0, C.byref(total), device))
+    keys = np.empty(max(1, total.value), np.int64)
+    _check(lib.frangi_gpu_seed_candidates_host(_ptr(J8), w, h, l, _ptr(lo), _ptr(hi), _ptr(n), _ptr(keys), keys.size,
+                                               C.byref(total), device))
+    return dict(layer_min=lo, layer_max=hi, n_max=n, keys=keys[:total.value].copy())
