@@ -236,10 +236,10 @@ class FrangiPlan:
     def sync(self):
         _check(self.lib.frangi_gpu_sync(self.handle))
 
-    def download(self, want_J8=False):
+    def download(self, want_J8=False, want_J=True, want_V=True):
         shp = (self.nz, self.h, self.w)
-        J = np.empty(shp, np.float32)
-        V = [np.empty(shp, np.uint8) for _ in range(3)]
+        J = np.empty(shp, np.float32) if want_J else None
+        V = [np.empty(shp, np.uint8) if want_V else None for _ in range(3)]
         J8 = np.empty(shp, np.uint8) if want_J8 else None
         sc = np.empty(shp, np.uint8) if (self.flags & FLAG_SCALE_IDX) else None
         dr = np.empty((3,) + shp, np.float32) if (self.flags & FLAG_DIR_F32) else None
