@@ -215,6 +215,8 @@ struct Slab {
     uint8_t *dVx = nullptr, *dVy = nullptr, *dVz = nullptr, *dScale = nullptr, *dJ8 = nullptr;
     float* dDir = nullptr;
     CUtensorMap tmF{}, tmFc{};   // TMA descriptors of dF: boxes of the full-eigen and of the compacting K3 kernel
+    CUtensorMap tmFxy{};         // TMA descriptor of dFxy: 64 x 1 x 1 row segments for the z pass
+    const float* dFxy0 = nullptr; // the pointer tmFxy was encoded with (views move dFxy and / or xb, the map stays)
     bool has_tm = false;
     int* dMinMax = nullptr;
     int* hMinMax = nullptr;   // pinned
@@ -365,6 +367,8 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     CK(cudaMalloc(&s.dI, (size_t)s.voxels));
     CK(cudaMalloc(&s.dFxy, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
     CK(cudaMalloc(&s.dF, sizeof(float) * (size_t)H->fplane * (s.fe - s.fb)));
+    RC(make_tile_map(&s.tmFxy, s.dFxy, H->w, H->h, s.xe - s.xb, H->fpitch, H->fplane, ZTile::COLS, 1));
+    s.dFxy0 = s.dFxy;
     if (H->w >= 5 && H->h >= 5 && H->l >= 5) {   // thinner volumes go to the shell kernel entirely (launch_voxel)
         RC(make_tile_map(&s.tmF, s.dF, H->w, H->h, s.fe - s.fb, H->fpitch, H->fplane, HessTile::PW, HessTile::PH));
         RC(make_tile_map(&s.tmFc, s.dF, H->w, H->h, s.fe - s.fb, H->fpitch, H->fplane, HessTileC::PW, HessTileC::PH));
@@ -421,6 +425,29 @@ int launch_zm_t(const ZParams& p, const GaussTaps& t, long long nblocks, cudaStr
     return 0;
 }
 
+template <int L, bool EXACT>
+int launch_zt_t(const CUtensorMap& tm, const ZParams& p, const GaussTaps& t, long long nwarps, cudaStream_t s)
+{
+    const long long nblocks = (nwarps + ZTile::WARPS - 1) / ZTile::WARPS;
+    if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+    gauss_z_tma_kernel<L, EXACT><<<(unsigned)nblocks, 32 * ZTile::WARPS, ZTile::SMEM_BYTES, s>>>(tm, p, t);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <bool EXACT>
+int launch_zt_e(int L, const CUtensorMap& tm, const ZParams& p, const GaussTaps& t, long long nwarps, cudaStream_t s)
+{
+    switch (L) {
+        case 3: return launch_zt_t<3, EXACT>(tm, p, t, nwarps, s);
+        case 6: return launch_zt_t<6, EXACT>(tm, p, t, nwarps, s);
+        case 9: return launch_zt_t<9, EXACT>(tm, p, t, nwarps, s);
+        case 12: return launch_zt_t<12, EXACT>(tm, p, t, nwarps, s);
+    }
+    return fail(FRANGI_GPU_EINVAL, "no TMA gauss_z instantiation for radius %d", L);
+}
+
 template <bool EXACT>
 int launch_zm_e(int L, const ZParams& p, const GaussTaps& t, long long nblocks, cudaStream_t s)
 {
@@ -442,6 +469,22 @@ int launch_z(frangi_gpu* H, Slab& s, const ScalePlan& sp)
     p.in_base = s.xb; p.in_count = s.xe - s.xb;
     p.out_base = s.fb; p.out_count = s.fe - s.fb;
     const bool fma = (H->flags & FRANGI_GPU_FLAG_FMA_SMOOTHING) != 0;
+    cudaStream_t st = s.s_main;
+#ifndef Z_TMA
+#define Z_TMA 1
+#endif
+    if (Z_TMA && sp.rz_t <= 12) {
+        // TMA form: one warp per 64-column row segment, one chunk per column unless that cannot fill the GPU
+        p.nxs = (H->w + ZTile::COLS - 1) / ZTile::COLS;
+        p.tm_base = s.xb - (int)((s.dFxy - s.dFxy0) / H->fplane);   // global plane of plane 0 of the tensor map
+        const long long cols = (long long)p.nxs * H->h;
+        long long nzc = std::max<long long>(1, std::min<long long>((148 * 32 + cols - 1) / cols, (p.out_count + 15) / 16));
+        p.zchunk = (int)((p.out_count + nzc - 1) / nzc);
+        nzc = (p.out_count + p.zchunk - 1) / p.zchunk;
+        p.nzc = (int)nzc;
+        if (fma) return launch_zt_e<false>(sp.rz_t, s.tmFxy, p, sp.tz, cols * nzc, st);
+        return launch_zt_e<true>(sp.rz_t, s.tmFxy, p, sp.tz, cols * nzc, st);
+    }
     if (sp.rz_t <= 12) {
         // marching form: one chunk per column unless the plane alone cannot fill the GPU
         p.nxs = (H->w + 2 * ZM_THREADS - 1) / (2 * ZM_THREADS);

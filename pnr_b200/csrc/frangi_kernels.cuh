@@ -421,6 +421,7 @@ struct ZParams {
     int out_count;      // planes to produce
     int nzc, nxs;       // z chunks, x strips
     int zchunk;         // output planes per chunk (marching form)
+    int tm_base;        // gauss_z_tma_kernel: global plane of plane 0 of the tensor map (the slab's Fxy buffer)
 };
 
 template <int LZ, bool EXACT>
@@ -697,6 +698,106 @@ struct TileRing {
         if (o[4] == TILE::SLOTS * TILE::SLOT) o[4] = 0;
     }
 };
+
+// ---------------------------------------------------------------------------
+// K2 (TMA form, radius <= 12): the same register sliding window as gauss_z_march_kernel, but the
+// loads are bulk copies.  A WARP owns 64 adjacent x columns of one row and marches along z; lane 0
+// keeps DEPTH planes of the warp's 256-byte row segment in flight with cp.async.bulk.tensor on a
+// (w, h, planes) tensor map of Fxy (box 64 x 1 x 1, completion on one mbarrier per slot), every lane
+// picks its two columns out of the landed segment with one 64-bit shared load and pushes them into
+// its window.  Bytes in flight no longer depend on registers or on resident threads (DEPTH x 256 B per
+// warp), so the kernel reaches the HBM rate at every radius, and two warps with 16 KB of shared
+// memory keep 8 KB in flight -- small enough to run NEXT to a K3 CTA set on the same SM.
+// Warps are independent (no __syncthreads): slot reuse is ordered by __syncwarp.
+// Arithmetic and accumulation order are those of gauss_z_march_kernel (bit-identical results).
+// ---------------------------------------------------------------------------
+#ifndef ZT_DEPTH
+#define ZT_DEPTH 16
+#endif
+#ifndef ZT_WARPS
+#define ZT_WARPS 2
+#endif
+struct ZTile {
+    static constexpr int COLS = 64, DEPTH = ZT_DEPTH, WARPS = ZT_WARPS;
+    static constexpr int SMEM_BYTES = WARPS * DEPTH * (COLS * 4 + 8);
+};
+
+template <int LZ, bool EXACT>
+__global__ void __launch_bounds__(32 * ZTile::WARPS)
+gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ ZParams p, const __grid_constant__ GaussTaps taps)
+{
+    constexpr int Q = 2 * LZ + 1, D = ZTile::DEPTH;
+    extern __shared__ __align__(128) float zring[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * ZTile::WARPS + warp;     // (x strip, row, z chunk)
+    const int xs = (int)(item % p.nxs);
+    const long long rest = item / p.nxs;
+    const int y = (int)(rest % p.h);
+    const int zc = (int)(rest / p.h);
+    if (zc >= p.nzc) return;                                   // warp-uniform
+    const int x0 = xs * ZTile::COLS, x = x0 + 2 * lane;
+    const int t_begin = zc * p.zchunk;
+    const int nout = min(p.zchunk, p.out_count - t_begin);
+    const int zg0 = p.out_base + t_begin;
+    const int nin = nout + 2 * LZ;                             // inputs of the chunk: global planes zg0 - LZ + j, clamped
+    const float* ring = zring + warp * D * ZTile::COLS;
+    const uint32_t ring_s = smem_u32(ring);
+    const uint32_t bar_s = smem_u32(zring + ZTile::WARPS * D * ZTile::COLS) + warp * D * 8;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) mbar_init(bar_s + 8 * k, 1);
+        mbar_init_fence();
+    }
+    __syncwarp();
+    int islot = 0;                                             // lane 0: slot of the next copy
+    auto issue = [&](int j) {
+        // replicate clamp at the volume ends (frangi.cpp:758,776), then into the resident planes (only reached by
+        // window entries that feed outputs beyond out_count, which are never produced)
+        const int zs = clampi(clampi(zg0 - LZ + j, 0, p.l - 1), p.in_base, p.in_base + p.in_count - 1) - p.tm_base;
+        mbar_expect_tx(bar_s + 8 * islot, ZTile::COLS * 4);
+        tma_load_3d(ring_s + islot * ZTile::COLS * 4, &tm, bar_s + 8 * islot, x0, y, zs);
+        islot = islot + 1 == D ? 0 : islot + 1;
+    };
+    if (lane == 0)
+        for (int j = 0; j < min(D, nin); ++j) issue(j);
+    int slot = 0;
+    uint32_t par = 0;
+    auto next = [&](int j) {                                   // input j of the chunk, this lane's two columns
+        mbar_wait(bar_s + 8 * slot, par);
+        const float2 v = *reinterpret_cast<const float2*>(ring + slot * ZTile::COLS + 2 * lane);
+        __syncwarp();                                          // every lane has its copy: the slot may be refilled
+        if (lane == 0 && j + D < nin) issue(j + D);
+        if (++slot == D) { slot = 0; par ^= 1u; }
+        return v;
+    };
+    float2* __restrict__ dst = reinterpret_cast<float2*>(p.out + ((long long)t_begin * p.fplane + (long long)y * p.fpitch + x));
+    const long long plane2 = p.fplane / 2;
+    const bool store = x < p.w;
+    float2 win[Q];
+#pragma unroll
+    for (int j = 0; j < Q - 1; ++j) win[j] = next(j);
+    for (int t0 = 0; t0 < nout; t0 += Q) {
+#pragma unroll
+        for (int s = 0; s < Q; ++s) {
+            const int t = t0 + s;
+            if (t < nout) {
+                win[(s + Q - 1) % Q] = next(t + Q - 1);
+                float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int k = 0; k <= 2 * LZ; ++k) {
+                    const float2 v = win[(s + k) % Q];
+                    if (EXACT) {
+                        acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, taps.g[k]));
+                        acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, taps.g[k]));
+                    } else {
+                        acc = __ffma2_rn(v, make_float2(taps.g[k], taps.g[k]), acc);
+                    }
+                }
+                if (store) __stcs(dst + (long long)t * plane2, acc);
+            }
+        }
+    }
+}
 
 struct FView {
     const float* F;     // plane 0 = global plane base
