@@ -52,7 +52,13 @@ enum {
     /* frangi_gpu_create with ndev > 1: move halos with peer copies inside the process
      * instead of NCCL send/recv (implied when device_ids repeats a device, which is how
      * the slab decomposition is exercised on a single GPU) */
-    FRANGI_GPU_FLAG_LOCAL_HALO = 8
+    FRANGI_GPU_FLAG_LOCAL_HALO = 8,
+    /* one-device handles with >= 2 scales: run the (HBM-bound) z pass of a scale on a second,
+     * low-priority stream beside the (issue-bound) xy pass of the next scale and the Hessian /
+     * eigen stage of the previous one; needs a second pair of intermediate buffers
+     * (+8 B/voxel).  Results are bit-identical.  Off by default: measured gain 1.7 %
+     * (DESIGN.md section 6), and multi-slab handles do not have it. */
+    FRANGI_GPU_FLAG_OVERLAP_Z = 16
 };
 
 /* ---- whole-volume handle, one process driving ndev devices ---------------

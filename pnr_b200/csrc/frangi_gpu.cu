@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -72,6 +73,9 @@ int fail(int code, const char* fmt, ...)
     } while (0)
 
 // ---- tap planning (host; mirrors frangi.cpp:651-680 in float32) -------------
+#ifndef Z_TMA
+#define Z_TMA 1      // z pass by the TMA warp-stream kernel (0: the register-prefetch marching kernel)
+#endif
 constexpr int kEvPerScale = 5;   // timing events recorded per scale (see collect())
 constexpr int kRadii[] = { 3, 6, 9, 12, 15, 18, 24, 30 };
 constexpr int kNumRadii = sizeof(kRadii) / sizeof(kRadii[0]);
@@ -217,6 +221,12 @@ struct Slab {
     CUtensorMap tmF{}, tmFc{};   // TMA descriptors of dF: boxes of the full-eigen and of the compacting K3 kernel
     CUtensorMap tmFxy{};         // TMA descriptor of dFxy: 64 x 1 x 1 row segments for the z pass
     const float* dFxy0 = nullptr; // the pointer tmFxy was encoded with (views move dFxy and / or xb, the map stays)
+    // overlapped schedule (one-slab handles, run_pipeline): a second Fxy / F buffer pair with its descriptors, the
+    // low-priority stream of the z pass, and per-kernel timing events (6 per scale and timing set)
+    float *dFxyB = nullptr, *dFB = nullptr;
+    CUtensorMap tmFB{}, tmFcB{}, tmFxyB{};
+    cudaStream_t s_aux = nullptr;
+    std::vector<cudaEvent_t> ev_ov;
     bool has_tm = false;
     int* dMinMax = nullptr;
     int* hMinMax = nullptr;   // pinned
@@ -246,6 +256,7 @@ struct frangi_gpu {
     bool local_halo = false;     // halos move by peer copies inside this process instead of NCCL
     int stream_chunk = -1;       // frangi_gpu_run: planes per pipelined chunk; 0 = off, -1 = automatic
     bool last_streamed = false;  // the last run recorded no per-class events
+    bool overlap = false;        // one-slab handle on the overlapped schedule (see run_pipeline)
     int timing_depth = 1;        // event sets kept per slab
     long long runs_recorded = 0; // runs since the last frangi_gpu_timing_depth call
     float last_ms[8] = { 0 };
@@ -266,6 +277,9 @@ void free_slab(Slab& s)
     if (s.ev_halo) cudaEventDestroy(s.ev_halo);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     cudaFree(s.dGather);
+    cudaFree(s.dFxyB); cudaFree(s.dFB);
+    for (auto e : s.ev_ov) cudaEventDestroy(e);
+    if (s.s_aux) cudaStreamDestroy(s.s_aux);
     if (s.s_main) cudaStreamDestroy(s.s_main);
     if (s.s_comm) cudaStreamDestroy(s.s_comm);
     if (s.s_h2d) cudaStreamDestroy(s.s_h2d);
@@ -354,7 +368,10 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     s.xe = std::min(s.fe + H->rz_max, H->l);
     s.voxels = (long long)H->w * H->h * (ze - zb);
     CK(cudaSetDevice(dev));
-    CK(cudaStreamCreateWithFlags(&s.s_main, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));     // numerically lowest = highest priority
+    CK(cudaStreamCreateWithPriority(&s.s_main, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&s.s_aux, cudaStreamNonBlocking, prio_lo));
     CK(cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s.s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s.s_d2h, cudaStreamNonBlocking));
@@ -369,6 +386,15 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     CK(cudaMalloc(&s.dF, sizeof(float) * (size_t)H->fplane * (s.fe - s.fb)));
     RC(make_tile_map(&s.tmFxy, s.dFxy, H->w, H->h, s.xe - s.xb, H->fpitch, H->fplane, ZTile::COLS, 1));
     s.dFxy0 = s.dFxy;
+    if (H->overlap) {
+        CK(cudaMalloc(&s.dFxyB, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
+        CK(cudaMalloc(&s.dFB, sizeof(float) * (size_t)H->fplane * (s.fe - s.fb)));
+        RC(make_tile_map(&s.tmFxyB, s.dFxyB, H->w, H->h, s.xe - s.xb, H->fpitch, H->fplane, ZTile::COLS, 1));
+        RC(make_tile_map(&s.tmFB, s.dFB, H->w, H->h, s.fe - s.fb, H->fpitch, H->fplane, HessTile::PW, HessTile::PH));
+        RC(make_tile_map(&s.tmFcB, s.dFB, H->w, H->h, s.fe - s.fb, H->fpitch, H->fplane, HessTileC::PW, HessTileC::PH));
+        s.ev_ov.resize(6 * H->scales.size());
+        for (auto& e : s.ev_ov) CK(cudaEventCreate(&e));
+    }
     if (H->w >= 5 && H->h >= 5 && H->l >= 5) {   // thinner volumes go to the shell kernel entirely (launch_voxel)
         RC(make_tile_map(&s.tmF, s.dF, H->w, H->h, s.fe - s.fb, H->fpitch, H->fplane, HessTile::PW, HessTile::PH));
         RC(make_tile_map(&s.tmFc, s.dF, H->w, H->h, s.fe - s.fb, H->fpitch, H->fplane, HessTileC::PW, HessTileC::PH));
@@ -460,7 +486,7 @@ int launch_zm_e(int L, const ZParams& p, const GaussTaps& t, long long nblocks, 
     return fail(FRANGI_GPU_EINVAL, "no marching gauss_z instantiation for radius %d", L);
 }
 
-int launch_z(frangi_gpu* H, Slab& s, const ScalePlan& sp)
+int launch_z(frangi_gpu* H, Slab& s, const ScalePlan& sp, cudaStream_t stream = nullptr)
 {
     ZParams p;
     p.in = s.dFxy; p.out = s.dF;
@@ -469,10 +495,7 @@ int launch_z(frangi_gpu* H, Slab& s, const ScalePlan& sp)
     p.in_base = s.xb; p.in_count = s.xe - s.xb;
     p.out_base = s.fb; p.out_count = s.fe - s.fb;
     const bool fma = (H->flags & FRANGI_GPU_FLAG_FMA_SMOOTHING) != 0;
-    cudaStream_t st = s.s_main;
-#ifndef Z_TMA
-#define Z_TMA 1
-#endif
+    cudaStream_t st = stream ? stream : s.s_main;
     if (Z_TMA && sp.rz_t <= 12) {
         // TMA form: one warp per 64-column row segment, one chunk per column unless that cannot fill the GPU
         p.nxs = (H->w + ZTile::COLS - 1) / ZTile::COLS;
@@ -780,6 +803,47 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
                 }
                 CK(cudaEventRecord(ev[5], s.s_main));
             }
+        } else if (H->overlap) {
+            // One slab, overlapped schedule.  The z pass is HBM-bound and the stages around it are issue-bound, so
+            // it runs on a low-priority stream NEXT to them: K2(si) beside K1(si+1), K2(si+1) beside K3(si).
+            // Two Fxy / F buffer pairs alternate by scale.  Main stream: K1(0) | K1(1) K3(0) | K1(2) K3(1) | ... ;
+            // aux stream: K2(si) after K1(si).  Buffer reuse is ordered by the main stream itself: K1(si+1) follows
+            // K3(si-1), which waited for K2(si-1) (last reader of that Fxy), and K2(si) follows K1(si), which
+            // follows K3(si-2) (last reader of that F).
+            Slab& s = H->slabs[0];
+            CK(cudaSetDevice(s.dev));
+            cudaEvent_t* eo = s.ev_ov.data() + 6 * si;          // K1 start/end, K2 start/end, K3 start/end
+            auto buf = [&](int q) {
+                Slab v = s;
+                if (q & 1) { v.dFxy = s.dFxyB; v.dFxy0 = s.dFxyB; v.dF = s.dFB; v.tmFxy = s.tmFxyB; v.tmF = s.tmFB; v.tmFc = s.tmFcB; }
+                return v;
+            };
+            if (si == 0) {
+                Slab v = buf(0);
+                CK(cudaEventRecord(eo[0], s.s_main));
+                RC(launch_xy(H, v, sp, I_own[0], s.zb, s.ze));
+                CK(cudaEventRecord(eo[1], s.s_main));
+            }
+            {
+                Slab v = buf(si);
+                CK(cudaStreamWaitEvent(s.s_aux, eo[1], 0));
+                CK(cudaEventRecord(eo[2], s.s_aux));
+                RC(launch_z(H, v, sp, s.s_aux));
+                CK(cudaEventRecord(eo[3], s.s_aux));
+            }
+            if (si + 1 < S) {
+                Slab v = buf(si + 1);
+                CK(cudaEventRecord(eo[6], s.s_main));
+                RC(launch_xy(H, v, H->scales[si + 1], I_own[0], s.zb, s.ze));
+                CK(cudaEventRecord(eo[7], s.s_main));
+            }
+            {
+                Slab v = buf(si);
+                CK(cudaStreamWaitEvent(s.s_main, eo[3], 0));
+                CK(cudaEventRecord(eo[4], s.s_main));
+                RC(launch_voxel(H, v, sp, si));
+                CK(cudaEventRecord(eo[5], s.s_main));
+            }
         } else {
             Slab& s = H->slabs[0];
             CK(cudaSetDevice(s.dev));
@@ -794,6 +858,7 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
             CK(cudaEventRecord(ev[5], s.s_main));
         }
     }
+    if (!multi && H->overlap) CK(cudaEventRecord(H->slabs[0].ev_time[kEvPerScale * S], H->slabs[0].s_main));
     // global Jmin / Jmax across slabs, then the 8-bit normalisation
     if (multi && H->local_halo) {
         // gather every slab's pair on slab 0, reduce there, hand the result back
@@ -877,7 +942,15 @@ int collect(frangi_gpu* H, float* Jmin, float* Jmax)
     for (int r = 0; r < nsets; ++r) {
         const cudaEvent_t* ev = s0.ev_all.data() + (size_t)r * (kEvPerScale * S + 2);
         float t;
-        for (int si = 0; si < S; ++si) {
+        for (int si = 0; si < S && H->overlap; ++si) {
+            // overlapped schedule: every kernel class has its own start / end pair (the classes run side by side, their
+            // sum exceeds the step); the per-kernel events are those of the LAST run
+            const cudaEvent_t* e = s0.ev_ov.data() + 6 * si;
+            CK(cudaEventElapsedTime(&t, e[0], e[1])); H->last_ms[0] += t;
+            CK(cudaEventElapsedTime(&t, e[2], e[3])); H->last_ms[1] += t;
+            CK(cudaEventElapsedTime(&t, e[4], e[5])); H->last_ms[2] += t;
+        }
+        for (int si = 0; si < S && !H->overlap; ++si) {
             const cudaEvent_t* e = ev + kEvPerScale * si;     // e[0] = end of the previous scale (or run start)
             CK(cudaEventElapsedTime(&t, e[0], e[1])); H->last_ms[0] += t;   // xy smoothing
             CK(cudaEventElapsedTime(&t, e[1], e[2])); H->last_ms[1] += t;   // z smoothing (interior part when multi-slab)
@@ -1066,6 +1139,9 @@ FRANGI_API int frangi_gpu_create(frangi_gpu_t** out, const float* sigmas, int ns
     int nuse = std::min(ndev, std::max(1, l / min_thick));
     H->nslabs_total = nuse;
     H->slabs.resize(nuse);
+    // one slab, several scales, TMA z pass available for every radius: the overlapped schedule (run_pipeline)
+    H->overlap = (flags & FRANGI_GPU_FLAG_OVERLAP_Z) && nuse == 1 && nsig >= 2 && Z_TMA;
+    for (const auto& sp : H->scales) H->overlap = H->overlap && sp.rz_t <= 12;
     std::vector<int> devs(nuse);
     for (int k = 0; k < nuse; ++k) devs[k] = device_ids ? device_ids[k] : k;
     for (int k = 0; k < nuse && !rc; ++k) {

@@ -30,6 +30,7 @@ FLAG_FMA_SMOOTHING = 1
 FLAG_DIR_F32 = 2
 FLAG_SCALE_IDX = 4
 FLAG_LOCAL_HALO = 8
+FLAG_OVERLAP_Z = 16
 
 _u8p = C.POINTER(C.c_uint8)
 _f32p = C.POINTER(C.c_float)

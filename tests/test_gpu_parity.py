@@ -4,6 +4,7 @@ BASELINE.json:north_star and are written in tests/parity.py."""
 import numpy as np
 import pytest
 
+import pnr_b200
 from pnr_b200 import FLAG_DIR_F32, FLAG_FMA_SMOOTHING, FLAG_SCALE_IDX, Frangi
 from pnr_b200.synth import make_volume, straight_tube
 from tests import parity
@@ -199,3 +200,21 @@ def test_repeatable_and_handle_reuse(oracle):
     for k in ("J", "Vx", "Vy", "Vz", "J8", "scale"):
         assert np.array_equal(a[k], c[k]), k
     assert not np.array_equal(a["J"], b["J"])
+
+
+def test_overlapped_schedule_is_bit_identical():
+    """FRANGI_GPU_FLAG_OVERLAP_Z: z pass on a second stream beside its neighbours, two buffer pairs -- same bits."""
+    from pnr_b200.frangi import FLAG_OVERLAP_Z
+    I = make_volume(160, 128, 72, seed=9)
+    outs = []
+    for flags in (0, FLAG_OVERLAP_Z):
+        p = pnr_b200.FrangiPlan(SIGS, 2.0, .5, .5, 500., False, 160, 128, 72, flags=flags)
+        p.set_stream_chunk(0)            # one-piece run: the schedule under test
+        for _ in range(2):               # twice: buffer reuse across runs
+            o = p.run(I, want_J8=True)
+        outs.append(o)
+        p.close()
+    a, b = outs
+    assert a["Jmax"] == b["Jmax"] and a["Jmin"] == b["Jmin"]
+    for k in ("J", "Vx", "Vy", "Vz", "J8"):
+        assert np.array_equal(a[k], b[k]), k
