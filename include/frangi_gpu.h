@@ -175,6 +175,21 @@ int frangi_gpu_seed_candidates_host(const uint8_t* J8_host, int w, int h, int l,
                                     uint8_t* layer_max, int* n_max, int64_t* keys, int64_t keys_cap,
                                     int64_t* n_keys, int device);
 
+/* ---- f4: the 2-D path ---------------------------------------------------------
+ * Replaces Frangi::frangi2d(I,w,h,l,J,Jmin,Jmax,Vx,Vy,Vz) (frangi.h:38, frangi.cpp:392-505;
+ * the plugin calls it for single-plane images, Advantra_plugin.cpp:2497) and
+ * Frangi::hessian2d(I,w,h,sig,Dyy,Dxy,Dxx) (frangi.h:40, frangi.cpp:507-560) over the 2-D
+ * imgaussian (frangi.cpp:562-645).  Host buffers of w*h elements, handle-less; beta_one /
+ * beta_two are the constructor's 2-D constants (frangi.h:13-14).  Vz is filled with 0 as
+ * the reference does.  flags is accepted for symmetry; the 2-D path always smooths with the
+ * reference's separately rounded multiply and add (FRANGI_GPU_FLAG_FMA_SMOOTHING is ignored). */
+int frangi_gpu_frangi2d(const uint8_t* I_host, int w, int h, const float* sigmas, int nsig,
+                        float beta_one, float beta_two, int blackwhite, float* J_host, float* Jmin,
+                        float* Jmax, uint8_t* Vx_host, uint8_t* Vy_host, uint8_t* Vz_host, int device,
+                        unsigned flags);
+int frangi_gpu_hessian2d(const uint8_t* I_host, int w, int h, float sigma, float* Dyy, float* Dxy,
+                         float* Dxx, int device, unsigned flags);
+
 /* ---- utilities --------------------------------------------------------------*/
 void* frangi_gpu_host_alloc(size_t bytes); /* pinned host memory (NULL on failure) */
 void frangi_gpu_host_free(void* p);

@@ -79,6 +79,11 @@ class Oracle:
         L.oracle_extract_seeds.restype = C.c_long
         L.oracle_extract_seeds.argtypes = [C.c_double, _u8p, C.c_int, C.c_int, C.c_int,
                                            _u8p, _u8p, _u8p, _f32p, C.c_long]
+        L.oracle_frangi2d.restype = C.c_int
+        L.oracle_frangi2d.argtypes = [_u8p, C.c_int, C.c_int, _f32p, C.c_int, C.c_float, C.c_float, C.c_int,
+                                      _f32p, _f32p, _f32p, _u8p, _u8p, _u8p]
+        L.oracle_hessian2d.restype = C.c_int
+        L.oracle_hessian2d.argtypes = [_u8p, C.c_int, C.c_int, C.c_float, _f32p, _f32p, _f32p, _f32p]
         L.oracle_seed_candidates.restype = C.c_long
         L.oracle_seed_candidates.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, C.POINTER(C.c_int),
                                              C.POINTER(C.c_int64), C.c_long]
@@ -160,6 +165,29 @@ class Oracle:
         return out[:n].copy()
 
 
+    def frangi2d(self, I, sigmas, beta_one=0.5, beta_two=15.0, blackwhite=False):
+        """Frangi::frangi2d (frangi.cpp:392-505) on a uint8 image [h][w]."""
+        I = np.ascontiguousarray(I, np.uint8)
+        h, w = I.shape
+        s = np.ascontiguousarray(sigmas, np.float32)
+        J = np.empty(I.shape, np.float32)
+        V = [np.empty(I.shape, np.uint8) for _ in range(3)]
+        lo = np.zeros(1, np.float32); hi = np.zeros(1, np.float32)
+        rc = self.lib.oracle_frangi2d(_p(I, _u8p), w, h, _p(s, _f32p), len(s), beta_one, beta_two, int(blackwhite),
+                                      _p(J, _f32p), _p(lo, _f32p), _p(hi, _f32p), _p(V[0], _u8p), _p(V[1], _u8p),
+                                      _p(V[2], _u8p))
+        if rc:
+            raise RuntimeError("oracle_frangi2d failed")
+        return dict(J=J, Jmin=float(lo[0]), Jmax=float(hi[0]), Vx=V[0], Vy=V[1], Vz=V[2])
+
+    def hessian2d(self, I, sigma):
+        I = np.ascontiguousarray(I, np.uint8)
+        h, w = I.shape
+        D = {k: np.empty(I.shape, np.float32) for k in ("Dyy", "Dxy", "Dxx", "F")}
+        self.lib.oracle_hessian2d(_p(I, _u8p), w, h, sigma, _p(D["Dyy"], _f32p), _p(D["Dxy"], _f32p),
+                                  _p(D["Dxx"], _f32p), _p(D["F"], _f32p))
+        return D
+
     def seed_candidates(self, J8):
         """The pre-pass of extractSeeds (seed.cpp:574-632): per-layer range, candidate counts, ranked keys."""
         J8, w, h, l = _check_vol(J8)
@@ -195,6 +223,13 @@ class Reference:
         L.ref_extract_seeds.restype = C.c_long
         L.ref_extract_seeds.argtypes = [C.c_double, _u8p, C.c_int, C.c_int, C.c_int,
                                         _u8p, _u8p, _u8p, _f32p, C.c_long]
+        self.has_2d = hasattr(L, "ref_frangi2d")
+        if self.has_2d:
+            L.ref_frangi2d.restype = None
+            L.ref_frangi2d.argtypes = [_u8p, C.c_int, C.c_int, _f32p, C.c_int, C.c_float, C.c_float, C.c_int,
+                                       _f32p, _f32p, _f32p, _u8p, _u8p, _u8p]
+            L.ref_hessian2d.restype = None
+            L.ref_hessian2d.argtypes = [_u8p, C.c_int, C.c_int, C.c_float, _f32p, _f32p, _f32p]
         self.has_trace = hasattr(L, "ref_trace")
         if self.has_trace:
             L.ref_trace.restype = C.c_int
@@ -248,6 +283,24 @@ class Reference:
         if n < 0 or n > cap:
             raise RuntimeError(f"ref_extract_seeds returned {n} (cap {cap})")
         return out[:n].copy()
+
+    def frangi2d(self, I, sigmas, beta_one=0.5, beta_two=15.0, blackwhite=False):
+        I = np.ascontiguousarray(I, np.uint8)
+        h, w = I.shape
+        s = np.ascontiguousarray(sigmas, np.float32)
+        J = np.empty(I.shape, np.float32)
+        V = [np.empty(I.shape, np.uint8) for _ in range(3)]
+        lo, hi = C.c_float(), C.c_float()
+        self.lib.ref_frangi2d(_p(I, _u8p), w, h, _p(s, _f32p), len(s), beta_one, beta_two, int(blackwhite),
+                              _p(J, _f32p), C.byref(lo), C.byref(hi), _p(V[0], _u8p), _p(V[1], _u8p), _p(V[2], _u8p))
+        return dict(J=J, Jmin=lo.value, Jmax=hi.value, Vx=V[0], Vy=V[1], Vz=V[2])
+
+    def hessian2d(self, I, sigma):
+        I = np.ascontiguousarray(I, np.uint8)
+        h, w = I.shape
+        D = {k: np.empty(I.shape, np.float32) for k in ("Dyy", "Dxy", "Dxx")}
+        self.lib.ref_hessian2d(_p(I, _u8p), w, h, sigma, _p(D["Dyy"], _f32p), _p(D["Dxy"], _f32p), _p(D["Dxx"], _f32p))
+        return D
 
     def trace(self, I, J8, Vx, Vy, Vz, sigmas, tolerance=5.0, znccth=0.3, kappa=3.0, step=2, ni=200, np_=20,
               zdist=2.0, nodepervol=4, max_traces=5000):

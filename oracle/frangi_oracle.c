@@ -518,3 +518,129 @@ ORACLE_API void oracle_j_to_j8(const float *J, int64_t total, float Jmin, float 
         J8[i] = (uint8_t)v;
     }
 }
+
+/* ------------------------------------------------------------------------ */
+/* 2-D path: Frangi::frangi2d (frangi.cpp:392-505) over    */
+/* hessian2d (:507-560) over the 2-D imgaussian (:562-645).  The reference's  */
+/* mixed float / double arithmetic is kept operation by operation: pow(x, 2)  */
+/* on a float is a double square, `.5 * float` is a double product stored to  */
+/* float, exp / sqrt / abs on floats are the float overloads.                 */
+/* ------------------------------------------------------------------------ */
+static void smooth2d(const uint8_t *I, int w, int h, float sigma, float *F)
+{
+    /* frangi.cpp:562-645: same taps as the 3-D filter (:566-577), x pass u8 -> K, y pass K -> F,
+     * float32 accumulation from zero in ascending tap order, replicate clamp */
+    const int L = oracle_gauss_radius(sigma);
+    float *g = (float *)malloc(sizeof(float) * (size_t)(2 * L + 1));
+    float *K = (float *)malloc(sizeof(float) * (size_t)w * h);
+    oracle_gauss_taps(sigma, L, g);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float acc = 0.0f;
+            for (int k = -L; k <= L; ++k) {
+                int xs = x + k < 0 ? 0 : (x + k > w - 1 ? w - 1 : x + k);
+                acc += (float)(int)I[(size_t)y * w + xs] * g[k + L];
+            }
+            K[(size_t)y * w + x] = acc;
+        }
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float acc = 0.0f;
+            for (int k = -L; k <= L; ++k) {
+                int ys = y + k < 0 ? 0 : (y + k > h - 1 ? h - 1 : y + k);
+                acc += K[(size_t)ys * w + x] * g[k + L];
+            }
+            F[(size_t)y * w + x] = acc;
+        }
+    free(g); free(K);
+}
+
+/* first difference of V along an axis with the reference's face rules (frangi.cpp:516-520 etc.) */
+static float diff2d(const float *V, int w, int h, int x, int y, int along_y)
+{
+    if (along_y) {
+        if (y == 0) return V[(size_t)(y + 1) * w + x] - V[(size_t)y * w + x];
+        if (y < h - 1) return (float)(.5 * (V[(size_t)(y + 1) * w + x] - V[(size_t)(y - 1) * w + x]));
+        return V[(size_t)y * w + x] - V[(size_t)(y - 1) * w + x];
+    }
+    if (x == 0) return V[(size_t)y * w + x + 1] - V[(size_t)y * w + x];
+    if (x < w - 1) return (float)(.5 * (V[(size_t)y * w + x + 1] - V[(size_t)y * w + x - 1]));
+    return V[(size_t)y * w + x] - V[(size_t)y * w + x - 1];
+}
+
+/* Dyy, Dxy, Dxx of one scale (frangi.cpp:507-560); F_out (nullable) receives the smoothed image */
+ORACLE_API int oracle_hessian2d(const uint8_t *I, int w, int h, float sigma, float *Dyy, float *Dxy, float *Dxx, float *F_out)
+{
+    const size_t n = (size_t)w * h;
+    float *F = (float *)malloc(sizeof(float) * n), *DD = (float *)malloc(sizeof(float) * n);
+    if (!F || !DD) { free(F); free(DD); return -1; }
+    smooth2d(I, w, h, sigma, F);
+    const float s2 = sigma * sigma;
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) DD[(size_t)y * w + x] = diff2d(F, w, h, x, y, 1);
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) Dyy[(size_t)y * w + x] = diff2d(DD, w, h, x, y, 1) * s2;
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) DD[(size_t)y * w + x] = diff2d(F, w, h, x, y, 0);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            Dxx[(size_t)y * w + x] = diff2d(DD, w, h, x, y, 0) * s2;
+            Dxy[(size_t)y * w + x] = diff2d(DD, w, h, x, y, 1) * s2;
+        }
+    if (F_out) memcpy(F_out, F, sizeof(float) * n);
+    free(F); free(DD);
+    return 0;
+}
+
+static uint8_t dir_code2d(float c, float n)
+{
+    /* frangi.cpp:457-459: round((((c/n)+1)/2)*255.0), clamped; a 0/0 direction converts to a negative int -> 0 */
+    float q = ((c / n) + 1) / 2;
+    double r = round((double)q * 255.0);
+    if (!(r == r)) return 0;
+    int val = (int)r;
+    return (uint8_t)(val < 0 ? 0 : (val > 255 ? 255 : val));
+}
+
+ORACLE_API int oracle_frangi2d(const uint8_t *I, int w, int h, const float *sigmas, int nsig, float beta_one, float beta_two,
+                               int blackwhite, float *J, float *Jmin_out, float *Jmax_out, uint8_t *Vx, uint8_t *Vy, uint8_t *Vz)
+{
+    const size_t n = (size_t)w * h;
+    float *Dxx = (float *)malloc(sizeof(float) * n), *Dxy = (float *)malloc(sizeof(float) * n), *Dyy = (float *)malloc(sizeof(float) * n);
+    if (!Dxx || !Dxy || !Dyy) { free(Dxx); free(Dxy); free(Dyy); return -1; }
+    const float beta = (float)(2 * ((double)beta_one * (double)beta_one));   /* :411-412 */
+    const float c = (float)(2 * ((double)beta_two * (double)beta_two));
+    float Jmin = FLT_MAX, Jmax = -FLT_MAX;
+    for (int si = 0; si < nsig; ++si) {
+        oracle_hessian2d(I, w, h, sigmas[si], Dyy, Dxy, Dxx, NULL);
+        for (size_t i = 0; i < n; ++i) {
+            float d = Dxx[i] - Dyy[i];
+            float tmp = (float)sqrt((double)d * (double)d + 4 * ((double)Dxy[i] * (double)Dxy[i]));      /* :425 */
+            float v2x = 2 * Dxy[i];
+            float v2y = Dyy[i] - Dxx[i] + tmp;
+            float mag = (float)sqrt((double)v2x * (double)v2x + (double)v2y * (double)v2y);            /* :430 */
+            if (mag > 0) { v2x /= mag; v2y /= mag; }
+            float v1x = -v2y, v1y = v2x;
+            float mu1 = (float)(0.5 * (double)(Dxx[i] + Dyy[i] + tmp));                                 /* :440-441 */
+            float mu2 = (float)(0.5 * (double)(Dxx[i] + Dyy[i] - tmp));
+            int check = fabsf(mu1) < fabsf(mu2);                                                        /* :444 */
+            float L1 = check ? mu2 : mu1, L2 = check ? mu1 : mu2;
+            float Vecx = check ? v2x : v1x, Vecy = check ? v2y : v1y;
+            L1 = (L1 == 0) ? FLT_MIN : L1;
+            float q = L2 / L1;
+            float Rb = (float)((double)q * (double)q);
+            float S2 = (float)((double)L1 * (double)L1 + (double)L2 * (double)L2);
+            float v = expf(-Rb / beta) * (1 - expf(-S2 / c));                                           /* :454 */
+            if (blackwhite) v = (L1 < 0) ? 0 : v; else v = (L1 > 0) ? 0 : v;
+            if (si == 0 || v > J[i]) {                                                                  /* :462-503 */
+                J[i] = v;
+                if (J[i] < Jmin) Jmin = J[i];
+                if (J[i] > Jmax) Jmax = J[i];
+                float Vecn = sqrtf(Vecx * Vecx + Vecy * Vecy);
+                Vx[i] = dir_code2d(Vecx, Vecn);
+                Vy[i] = dir_code2d(Vecy, Vecn);
+                Vz[i] = 0;
+            }
+        }
+    }
+    *Jmin_out = Jmin; *Jmax_out = Jmax;
+    free(Dxx); free(Dxy); free(Dyy);
+    return 0;
+}

@@ -93,6 +93,30 @@ void ref_frangi3d(unsigned char* I, int w, int h, int l, const float* sigmas, in
     *Jmax = hi;
 }
 
+// The 2-D path: Frangi::frangi2d (frangi.h:32, frangi.cpp:392) and Frangi::hessian2d (frangi.h:34, frangi.cpp:507)
+__attribute__((visibility("default")))
+void ref_frangi2d(unsigned char* I, int w, int h, const float* sigmas, int nsig, float beta_one, float beta_two, int blackwhite,
+                  float* J, float* Jmin, float* Jmax, unsigned char* Vx, unsigned char* Vy, unsigned char* Vz)
+{
+    QuietCout q;
+    std::vector<float> s(sigmas, sigmas + nsig);
+    Frangi f(s, 1.0f, .5f, .5f, 500.f, beta_one, beta_two);
+    f.blackwhite = blackwhite != 0;
+    float lo, hi;
+    f.frangi2d(I, w, h, 1, J, lo, hi, Vx, Vy, Vz);
+    *Jmin = lo;
+    *Jmax = hi;
+}
+
+__attribute__((visibility("default")))
+void ref_hessian2d(unsigned char* I, int w, int h, float sig, float* Dyy, float* Dxy, float* Dxx)
+{
+    QuietCout q;
+    std::vector<float> s(1, sig);
+    Frangi f(s, 1.0f, .5f, .5f, 500.f, .5f, 15.f);
+    f.hessian2d(I, w, h, sig, Dyy, Dxy, Dxx);
+}
+
 // Seeds are returned as rows of 6 floats (x, y, z, vx, vy, vz).  Returns the
 // number of seeds found; at most `cap` rows are written.
 __attribute__((visibility("default")))

@@ -7,10 +7,11 @@
 //
 // Same public field names, constructor and member signatures as the reference for
 // everything ON the path (frangi.h:8-24,33,35,42); every call forwards to the C-ABI
-// of include/frangi_gpu.h.  Members that are off the path (frangi2d, the soma
-// helpers imerode/imdilate/xy-imgaussian, the direction tables, the public
-// eigen-solver entry points) are not provided here: an integrator who needs them
-// keeps the reference's frangi.cpp under another class name.
+// of include/frangi_gpu.h.  The 2-D pair frangi2d / hessian2d (frangi.h:38,40) is
+// provided too.  Members that are off the path (the soma helpers imerode / imdilate /
+// xy-imgaussian, the direction tables, the public eigen-solver entry points) are not
+// provided here: an integrator who needs them keeps the reference's frangi.cpp under
+// another class name.
 //
 // Error behaviour: the reference's members return void and fail only by uncaught
 // std::bad_alloc; here a failed GPU call throws std::runtime_error carrying
@@ -29,7 +30,7 @@ public:
     float zdist;
     float alpha;
     float beta;
-    float BetaOne;   // 2-D only; kept so that the constructor signature matches
+    float BetaOne;   // 2-D only (frangi2d)
     float BetaTwo;   // 2-D only
     float C;
     bool blackwhite; // true: dark ridges, false: bright ridges (default, frangi.cpp:54)
@@ -55,6 +56,14 @@ public:
     // frangi.h:35
     void hessian3d(unsigned char* I, int w, int h, int l, float sig_, float zdist_,
                    float* Dzz, float* Dyy, float* Dyz, float* Dxx, float* Dxy, float* Dxz);
+
+    // frangi.h:38 -- single-plane images (the plugin's P == 1 branch, Advantra_plugin.cpp:2497); l is ignored as in
+    // the reference's arithmetic (it only scales the loop bounds there and is 1 at the call site)
+    void frangi2d(unsigned char* I, int w, int h, int l, float* J, float& Jmin, float& Jmax,
+                  unsigned char* Vx, unsigned char* Vy, unsigned char* Vz);
+
+    // frangi.h:40
+    void hessian2d(unsigned char* I, int w, int h, float sig_, float* Dyy, float* Dxy, float* Dxx);
 
     // frangi.h:42
     static void imgaussian(unsigned char* I, int w, int h, int l, float sig_, float zdist_, float* F);

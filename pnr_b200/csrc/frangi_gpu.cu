@@ -27,6 +27,7 @@
 
 #include "frangi_kernels.cuh"
 #include "seed_kernels.cuh"
+#include "frangi2d_kernels.cuh"
 #include "nccl_dyn.h"
 
 #define FRANGI_API extern "C" __attribute__((visibility("default")))
@@ -412,34 +413,42 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     return 0;
 }
 
-// xy smoothing of own planes [z0, z1) of slab s for one scale
-int launch_xy(frangi_gpu* H, Slab& s, const ScalePlan& sp, const uint8_t* I_own, int z0, int z1)
+// xy smoothing (K1) of nz dense planes I -> out
+int launch_xy_planes(const uint8_t* I, float* out, int w, int h, int nz, int fpitch, long long fplane, const ScalePlan& sp,
+                     unsigned flags, cudaStream_t st)
 {
-    if (z1 <= z0) return 0;
+    if (nz <= 0) return 0;
     XYParams p;
-    p.I = I_own + (long long)(z0 - s.zb) * H->w * H->h;
-    p.out = s.dFxy + (long long)(z0 - s.xb) * H->fplane;
-    p.w = H->w; p.h = H->h; p.nz = z1 - z0;
-    p.fpitch = H->fpitch; p.fplane = H->fplane;
-    p.nstrips = (H->w + 255) / 256;
+    p.I = I; p.out = out;
+    p.w = w; p.h = h; p.nz = nz;
+    p.fpitch = fpitch; p.fplane = fplane;
+    p.nstrips = (w + 255) / 256;
     // enough CTAs to fill 148 SMs a few times over, else split y into segments
     const long long want = 148 * 4;
     const long long per_seg = (long long)p.nstrips * p.nz;
-    int nsegs = (int)std::min<long long>((want + per_seg - 1) / per_seg, (H->h + 31) / 32);
+    int nsegs = (int)std::min<long long>((want + per_seg - 1) / per_seg, (h + 31) / 32);
     if (nsegs < 1) nsegs = 1;
-    int seg_h = ((H->h + nsegs - 1) / nsegs + 15) / 16 * 16;
+    int seg_h = ((h + nsegs - 1) / nsegs + 15) / 16 * 16;
     p.seg_h = seg_h;
-    p.nsegs = (H->h + seg_h - 1) / seg_h;
-    p.vec_ok = (H->w % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.I) & 3) == 0);
+    p.nsegs = (h + seg_h - 1) / seg_h;
+    p.vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.I) & 3) == 0);
     const long long nblocks = (long long)p.nstrips * p.nsegs * p.nz;
     if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
 #ifndef XY_FMA_PACKED
 #define XY_FMA_PACKED 1
 #endif
-    if (H->flags & FRANGI_GPU_FLAG_FMA_SMOOTHING)
-        return XY_FMA_PACKED ? launch_xy_fma(sp.rxy_t, p, sp.txy, (int)nblocks, s.s_main)
-                             : launch_xy_e<false>(sp.rxy_t, p, sp.txy, (int)nblocks, s.s_main);
-    return launch_xy_e<true>(sp.rxy_t, p, sp.txy, (int)nblocks, s.s_main);
+    if (flags & FRANGI_GPU_FLAG_FMA_SMOOTHING)
+        return XY_FMA_PACKED ? launch_xy_fma(sp.rxy_t, p, sp.txy, (int)nblocks, st)
+                             : launch_xy_e<false>(sp.rxy_t, p, sp.txy, (int)nblocks, st);
+    return launch_xy_e<true>(sp.rxy_t, p, sp.txy, (int)nblocks, st);
+}
+
+// xy smoothing of own planes [z0, z1) of slab s for one scale
+int launch_xy(frangi_gpu* H, Slab& s, const ScalePlan& sp, const uint8_t* I_own, int z0, int z1)
+{
+    if (z1 <= z0) return 0;
+    return launch_xy_planes(I_own + (long long)(z0 - s.zb) * H->w * H->h, s.dFxy + (long long)(z0 - s.xb) * H->fplane, H->w, H->h,
+                            z1 - z0, H->fpitch, H->fplane, sp, H->flags, s.s_main);
 }
 
 template <int L, bool EXACT>
@@ -1558,4 +1567,86 @@ FRANGI_API int frangi_gpu_seed_candidates_host(const uint8_t* J8_host, int w, in
     if (rc) return rc;
     if (keys && *n_keys > keys_cap) return fail(FRANGI_GPU_EINVAL, "seed_candidates: %lld keys, capacity %lld", (long long)*n_keys, (long long)keys_cap);
     return 0;
+}
+
+// ---- f4: the 2-D path, Frangi::frangi2d / hessian2d (frangi2d_kernels.cuh) -----------------------------
+namespace {
+struct Dev2D {     // device buffers of one 2-D call, freed on every path
+    uint8_t *I = nullptr, *V[3] = { nullptr, nullptr, nullptr };
+    float *F = nullptr, *J = nullptr, *D[3] = { nullptr, nullptr, nullptr };
+    int* mm = nullptr;
+    ~Dev2D() { cudaFree(I); cudaFree(F); cudaFree(J); cudaFree(mm); for (auto v : V) cudaFree(v); for (auto d : D) cudaFree(d); }
+};
+
+int run_2d(const uint8_t* I_host, int w, int h, const float* sigmas, int nsig, float beta_one, float beta_two, int blackwhite,
+           float* J_host, float* Jmin, float* Jmax, uint8_t* Vx, uint8_t* Vy, uint8_t* Vz, float* const* D_host, int device,
+           unsigned flags)
+{
+    if (!I_host || !sigmas || nsig < 1) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    if (w < 2 || h < 2 || (long long)w * h > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "frangi2d needs 2 <= w, h (got %d, %d)", w, h);
+    RC(check_device(device));
+    CK(cudaSetDevice(device));
+    const int fpitch = (w + 31) / 32 * 32;
+    const size_t n = (size_t)w * h;
+    Dev2D d;
+    CK(cudaMalloc(&d.I, n));
+    CK(cudaMalloc(&d.F, sizeof(float) * (size_t)fpitch * h));
+    CK(cudaMalloc(&d.J, sizeof(float) * n));
+    CK(cudaMalloc(&d.mm, 2 * sizeof(int)));
+    for (auto& v : d.V) CK(cudaMalloc(&v, n));
+    if (D_host) for (auto& q : d.D) CK(cudaMalloc(&q, sizeof(float) * n));
+    CK(cudaMemcpy(d.I, I_host, n, cudaMemcpyHostToDevice));
+    const int init[2] = { 0x7f7fffff, (int)0xff7fffffu };      // FLT_MAX, -FLT_MAX (frangi.cpp:414-415)
+    CK(cudaMemcpy(d.mm, init, sizeof init, cudaMemcpyHostToDevice));
+    for (int si = 0; si < nsig; ++si) {
+        if (!(sigmas[si] > 0)) return fail(FRANGI_GPU_EINVAL, "sigma[%d] must be > 0", si);
+        ScalePlan sp;
+        sp.sigma = sigmas[si]; sp.sigma2 = sigmas[si] * sigmas[si];
+        RC(plan_taps(sp.sigma, sp.rxy, sp.rxy_t, sp.txy));
+        // always the separately rounded smoothing: the 2-D measure (values up to 1, ratios of eigenvalues squared) does
+        // not keep the 1e-4 tolerance under fused multiply-add, and a single image has no speed to gain from it
+        RC(launch_xy_planes(d.I, d.F, w, h, 1, fpitch, (long long)fpitch * h, sp, flags & ~(unsigned)FRANGI_GPU_FLAG_FMA_SMOOTHING, 0));
+        F2DParams p;
+        p.F = d.F; p.w = w; p.h = h; p.fpitch = fpitch;
+        p.sigma2 = sp.sigma2;
+        p.beta = (float)(2 * ((double)beta_one * (double)beta_one));
+        p.c = (float)(2 * ((double)beta_two * (double)beta_two));
+        p.blackwhite = blackwhite; p.first = si == 0;
+        p.J = d.J; p.Vx = d.V[0]; p.Vy = d.V[1]; p.Vz = d.V[2];
+        for (int k = 0; k < 3; ++k) p.D[k] = D_host ? d.D[k] : nullptr;
+        p.minmax = d.mm;
+        frangi2d_pixel_kernel<<<dim3((w + 127) / 128, h), 128>>>(p);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaDeviceSynchronize());
+    if (D_host) {
+        for (int k = 0; k < 3; ++k) CK(cudaMemcpy(D_host[k], d.D[k], sizeof(float) * n, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    int mm[2];
+    CK(cudaMemcpy(mm, d.mm, sizeof mm, cudaMemcpyDeviceToHost));
+    if (Jmin) std::memcpy(Jmin, &mm[0], 4);
+    if (Jmax) std::memcpy(Jmax, &mm[1], 4);
+    if (J_host) CK(cudaMemcpy(J_host, d.J, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    uint8_t* const out[3] = { Vx, Vy, Vz };
+    for (int k = 0; k < 3; ++k) if (out[k]) CK(cudaMemcpy(out[k], d.V[k], n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+}  // namespace
+
+FRANGI_API int frangi_gpu_frangi2d(const uint8_t* I_host, int w, int h, const float* sigmas, int nsig, float beta_one, float beta_two,
+                                   int blackwhite, float* J_host, float* Jmin, float* Jmax, uint8_t* Vx_host, uint8_t* Vy_host,
+                                   uint8_t* Vz_host, int device, unsigned flags)
+{
+    return run_2d(I_host, w, h, sigmas, nsig, beta_one, beta_two, blackwhite, J_host, Jmin, Jmax, Vx_host, Vy_host, Vz_host, nullptr,
+                  device, flags);
+}
+
+FRANGI_API int frangi_gpu_hessian2d(const uint8_t* I_host, int w, int h, float sigma, float* Dyy, float* Dxy, float* Dxx, int device,
+                                    unsigned flags)
+{
+    if (!Dyy || !Dxy || !Dxx) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    float* const D[3] = { Dyy, Dxy, Dxx };
+    return run_2d(I_host, w, h, &sigma, 1, .5f, 15.f, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, D, device, flags);
 }

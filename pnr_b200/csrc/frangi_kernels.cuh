@@ -288,7 +288,10 @@ __device__ __forceinline__ void xy_fma_ypass(const float* s_ring, const GaussTap
 }
 
 template <int L>
-__global__ void __launch_bounds__(256, (L <= 9 ? 3 : 2))
+#ifndef XY_FMA_CTAS3_MAXL
+#define XY_FMA_CTAS3_MAXL 12     // radii up to this run 3 CTAs per SM (<= 85 registers), larger ones 2
+#endif
+__global__ void __launch_bounds__(256, (L <= XY_FMA_CTAS3_MAXL ? 3 : 2))
 gauss_xy_fma_kernel(const __grid_constant__ XYParams p, const __grid_constant__ GaussTaps taps)
 {
     using C = XYFmaCfg<L>;

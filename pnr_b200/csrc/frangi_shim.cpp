@@ -70,6 +70,26 @@ void Frangi::hessian3d(unsigned char* I, int w, int h, int l, float sig_, float 
     if (rc) raise("frangi_gpu_hessian3d", rc);
 }
 
+void Frangi::frangi2d(unsigned char* I, int w, int h, int l, float* J, float& Jmin, float& Jmax,
+                      unsigned char* Vx, unsigned char* Vy, unsigned char* Vz)
+{
+    if (l != 1) throw std::runtime_error("Frangi::frangi2d: the image must be a single plane (l == 1)");
+    const int dev = devices.empty() ? 0 : devices[0];
+    float lo = 0, hi = 0;
+    const int rc = frangi_gpu_frangi2d(I, w, h, sig.data(), (int)sig.size(), BetaOne, BetaTwo, blackwhite ? 1 : 0, J, &lo, &hi,
+                                       Vx, Vy, Vz, dev, flags & FRANGI_GPU_FLAG_FMA_SMOOTHING);
+    if (rc) raise("frangi_gpu_frangi2d", rc);
+    Jmin = lo;
+    Jmax = hi;
+}
+
+void Frangi::hessian2d(unsigned char* I, int w, int h, float sig_, float* Dyy, float* Dxy, float* Dxx)
+{
+    const int dev = devices.empty() ? 0 : devices[0];
+    const int rc = frangi_gpu_hessian2d(I, w, h, sig_, Dyy, Dxy, Dxx, dev, flags & FRANGI_GPU_FLAG_FMA_SMOOTHING);
+    if (rc) raise("frangi_gpu_hessian2d", rc);
+}
+
 void Frangi::imgaussian(unsigned char* I, int w, int h, int l, float sig_, float zdist_, float* F)
 {
     const int rc = frangi_gpu_imgaussian(I, w, h, l, sig_, zdist_, F, 0, 0);

@@ -71,6 +71,9 @@ SYMBOLS = {
     "frangi_gpu_seed_candidates": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int64, C.POINTER(C.c_int64)]),
     "frangi_gpu_seed_candidates_host": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_int64,
                                                   C.POINTER(C.c_int64), C.c_int]),
+    "frangi_gpu_frangi2d": (C.c_int, [_VP, C.c_int, C.c_int, _f32p, C.c_int, C.c_float, C.c_float, C.c_int, _VP, _f32p, _f32p,
+                                      _VP, _VP, _VP, C.c_int, C.c_uint]),
+    "frangi_gpu_hessian2d": (C.c_int, [_VP, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP, C.c_int, C.c_uint]),
     "frangi_gpu_host_alloc": (_VP, [C.c_size_t]),
     "frangi_gpu_host_free": (None, [_VP]),
     "frangi_gpu_device_count": (C.c_int, []),
@@ -324,6 +327,29 @@ class Frangi:
     def frangi3d_full(self, I, want_J8=True):
         I, w, h, l = _vol(I)
         return self._get_plan(w, h, l).run(I, want_J8=want_J8)
+
+    def frangi2d(self, I):
+        """Frangi::frangi2d (frangi.h:38) on a uint8 image [h][w]: dict(J, Jmin, Jmax, Vx, Vy, Vz)."""
+        I = np.ascontiguousarray(I, np.uint8)
+        if I.ndim != 2:
+            raise ValueError("image must be uint8 [h][w]")
+        h, w = I.shape
+        s = np.ascontiguousarray(self.sig, np.float32)
+        J = np.empty(I.shape, np.float32)
+        V = [np.empty(I.shape, np.uint8) for _ in range(3)]
+        lo, hi = C.c_float(), C.c_float()
+        _check(load_library().frangi_gpu_frangi2d(_ptr(I), w, h, s.ctypes.data_as(_f32p), len(s), self.BetaOne, self.BetaTwo,
+                                                  int(self.blackwhite), _ptr(J), C.byref(lo), C.byref(hi), _ptr(V[0]),
+                                                  _ptr(V[1]), _ptr(V[2]), self.devices[0], self.flags & FLAG_FMA_SMOOTHING))
+        return dict(J=J, Jmin=lo.value, Jmax=hi.value, Vx=V[0], Vy=V[1], Vz=V[2])
+
+    def hessian2d(self, I, sig):
+        I = np.ascontiguousarray(I, np.uint8)
+        h, w = I.shape
+        D = {k: np.empty(I.shape, np.float32) for k in ("Dyy", "Dxy", "Dxx")}
+        _check(load_library().frangi_gpu_hessian2d(_ptr(I), w, h, sig, _ptr(D["Dyy"]), _ptr(D["Dxy"]), _ptr(D["Dxx"]),
+                                                   self.devices[0], self.flags & FLAG_FMA_SMOOTHING))
+        return D
 
     @staticmethod
     def imgaussian(I, sig, zdist, device=0, flags=0):

@@ -94,5 +94,22 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def case_e_2d():
+    """case E: the 2-D path (Frangi::frangi2d / hessian2d) on one plane of a synthetic volume and its inverse."""
+    ref = Reference()
+    I = make_volume(96, 80, 8, seed=21, n_neurites=4)[3]
+    sig = [2.0, 3.0, 4.0]
+    R = ref.frangi2d(I, sig, 0.5, 15.0)
+    Rb = ref.frangi2d(255 - I, sig, 0.5, 15.0, blackwhite=True)
+    H = ref.hessian2d(I, 2.0)
+    np.savez_compressed(os.path.join(OUT, "case_e_frangi2d.npz"), I=I, sigmas=np.float32(sig), J=R["J"],
+                        Jmin=np.float32(R["Jmin"]), Jmax=np.float32(R["Jmax"]), Vx=R["Vx"], Vy=R["Vy"], Vz=R["Vz"],
+                        J_blackwhite=Rb["J"], **{"H_" + k: v for k, v in H.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "2d":     # only the 2-D case (leaves the other fixtures untouched)
+        case_e_2d()
+    else:
+        main()
+        case_e_2d()
