@@ -190,6 +190,17 @@ int frangi_gpu_frangi2d(const uint8_t* I_host, int w, int h, const float* sigmas
 int frangi_gpu_hessian2d(const uint8_t* I_host, int w, int h, float sigma, float* Dyy, float* Dxy,
                          float* Dxx, int device, unsigned flags);
 
+/* ---- f4, second part: the helpers of the plugin's soma branch -----------------------
+ * (Advantra_plugin.cpp:2426-2440, only reached with somaradius > 0).  Host buffers of
+ * w*h*l uint8, handle-less.  Replace, byte for byte:
+ *   Frangi::imerode(I,w,h,l,rad,E)   frangi.h:47, frangi.cpp:879-969   xy minimum, radius ceil(rad)
+ *   Frangi::imdilate(I,w,h,l,rad)    frangi.h:49, frangi.cpp:1110-1199 xy maximum, in place
+  *   Frangi::imgaussian(I,w,h,l,sig)  frangi.h:43, frangi.cpp:786-877   xy Gaussian in place; the y
+ *                                    pass accumulates into the unsigned char, truncating per tap */
+int frangi_gpu_imerode(const uint8_t* I_host, int w, int h, int l, float rad, uint8_t* E_host, int device);
+int frangi_gpu_imdilate(uint8_t* I_host, int w, int h, int l, float rad, int device);
+int frangi_gpu_imgaussian_xy(uint8_t* I_host, int w, int h, int l, float sig, int device);
+
 /* ---- utilities --------------------------------------------------------------*/
 void* frangi_gpu_host_alloc(size_t bytes); /* pinned host memory (NULL on failure) */
 void frangi_gpu_host_free(void* p);

@@ -84,6 +84,10 @@ class Oracle:
                                       _f32p, _f32p, _f32p, _u8p, _u8p, _u8p]
         L.oracle_hessian2d.restype = C.c_int
         L.oracle_hessian2d.argtypes = [_u8p, C.c_int, C.c_int, C.c_float, _f32p, _f32p, _f32p, _f32p]
+        L.oracle_morph_xy.restype = C.c_int
+        L.oracle_morph_xy.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _u8p]
+        L.oracle_imgaussian_xy_u8.restype = C.c_int
+        L.oracle_imgaussian_xy_u8.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float]
         L.oracle_seed_candidates.restype = C.c_long
         L.oracle_seed_candidates.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, C.POINTER(C.c_int),
                                              C.POINTER(C.c_int64), C.c_long]
@@ -188,6 +192,24 @@ class Oracle:
                                   _p(D["Dxx"], _f32p), _p(D["F"], _f32p))
         return D
 
+    def imerode(self, I, rad):
+        I, w, h, l = _check_vol(I)
+        out = np.empty_like(I)
+        self.lib.oracle_morph_xy(_p(I, _u8p), w, h, l, rad, 1, _p(out, _u8p))
+        return out
+
+    def imdilate(self, I, rad):
+        I, w, h, l = _check_vol(I)
+        out = np.empty_like(I)
+        self.lib.oracle_morph_xy(_p(I, _u8p), w, h, l, rad, 0, _p(out, _u8p))
+        return out
+
+    def imgaussian_xy(self, I, sigma):
+        I, w, h, l = _check_vol(I)
+        out = I.copy()
+        self.lib.oracle_imgaussian_xy_u8(_p(out, _u8p), w, h, l, sigma)
+        return out
+
     def seed_candidates(self, J8):
         """The pre-pass of extractSeeds (seed.cpp:574-632): per-layer range, candidate counts, ranked keys."""
         J8, w, h, l = _check_vol(J8)
@@ -230,6 +252,14 @@ class Reference:
                                        _f32p, _f32p, _f32p, _u8p, _u8p, _u8p]
             L.ref_hessian2d.restype = None
             L.ref_hessian2d.argtypes = [_u8p, C.c_int, C.c_int, C.c_float, _f32p, _f32p, _f32p]
+        self.has_soma = hasattr(L, "ref_imerode")
+        if self.has_soma:
+            L.ref_imerode.restype = None
+            L.ref_imerode.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float, _u8p]
+            L.ref_imdilate.restype = None
+            L.ref_imdilate.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float]
+            L.ref_imgaussian_xy.restype = None
+            L.ref_imgaussian_xy.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float]
         self.has_trace = hasattr(L, "ref_trace")
         if self.has_trace:
             L.ref_trace.restype = C.c_int
@@ -301,6 +331,24 @@ class Reference:
         D = {k: np.empty(I.shape, np.float32) for k in ("Dyy", "Dxy", "Dxx")}
         self.lib.ref_hessian2d(_p(I, _u8p), w, h, sigma, _p(D["Dyy"], _f32p), _p(D["Dxy"], _f32p), _p(D["Dxx"], _f32p))
         return D
+
+    def imerode(self, I, rad):
+        I, w, h, l = _check_vol(I)
+        out = np.empty_like(I)
+        self.lib.ref_imerode(_p(I, _u8p), w, h, l, rad, _p(out, _u8p))
+        return out
+
+    def imdilate(self, I, rad):
+        I, w, h, l = _check_vol(I)
+        out = I.copy()
+        self.lib.ref_imdilate(_p(out, _u8p), w, h, l, rad)
+        return out
+
+    def imgaussian_xy(self, I, sigma):
+        I, w, h, l = _check_vol(I)
+        out = I.copy()
+        self.lib.ref_imgaussian_xy(_p(out, _u8p), w, h, l, sigma)
+        return out
 
     def trace(self, I, J8, Vx, Vy, Vz, sigmas, tolerance=5.0, znccth=0.3, kappa=3.0, step=2, ni=200, np_=20,
               zdist=2.0, nodepervol=4, max_traces=5000):

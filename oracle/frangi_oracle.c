@@ -644,3 +644,79 @@ ORACLE_API int oracle_frangi2d(const uint8_t *I, int w, int h, const float *sigm
     free(Dxx); free(Dxy); free(Dyy);
     return 0;
 }
+
+/* ------------------------------------------------------------------------ */
+/* Soma helpers (second part; Advantra_plugin.cpp:2426-2440). */
+/* ------------------------------------------------------------------------ */
+/* Frangi::imerode(I,w,h,l,rad,E) (frangi.cpp:879-969) / Frangi::imdilate(I,w,h,l,rad) (:1110-1199): separable xy
+ * minimum / maximum over [c - ceil(rad), c + ceil(rad)], indices clamped (the three x ranges of the reference are the
+ * same clamped formula), x pass into a scratch volume, y pass from it. */
+ORACLE_API int oracle_morph_xy(const uint8_t *I, int w, int h, int l, float rad, int is_min, uint8_t *out)
+{
+    const int L = (int)ceilf(rad);
+    const size_t n = (size_t)w * h * l;
+    uint8_t *K = (uint8_t *)malloc(n);
+    if (!K) return -1;
+    for (int z = 0; z < l; ++z)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const uint8_t *row = I + ((size_t)z * h + y) * w;
+                uint8_t v = row[x];
+                for (int k = -L; k <= L; ++k) {
+                    int xs = x + k < 0 ? 0 : (x + k > w - 1 ? w - 1 : x + k);
+                    if (is_min ? row[xs] < v : row[xs] > v) v = row[xs];
+                }
+                K[((size_t)z * h + y) * w + x] = v;
+            }
+    for (int z = 0; z < l; ++z)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const uint8_t *pl = K + (size_t)z * h * w;
+                uint8_t v = pl[(size_t)y * w + x];
+                for (int k = -L; k <= L; ++k) {
+                    int ys = y + k < 0 ? 0 : (y + k > h - 1 ? h - 1 : y + k);
+                    uint8_t q = pl[(size_t)ys * w + x];
+                    if (is_min ? q < v : q > v) v = q;
+                }
+                out[((size_t)z * h + y) * w + x] = v;
+            }
+    free(K);
+    return 0;
+}
+
+/* Frangi::imgaussian(I,w,h,l,sig) (frangi.cpp:786-877): xy Gaussian of a uint8 volume in place.  The x pass
+ * accumulates in float32 (:806-838); the y pass accumulates INTO the unsigned char -- `I[i0] = 0; I[i0] += K*G` --
+ * so every tap is (unsigned char)((float)I[i0] + K*G) (:841-873). */
+ORACLE_API int oracle_imgaussian_xy_u8(uint8_t *I, int w, int h, int l, float sigma)
+{
+    const int L = oracle_gauss_radius(sigma);
+    const size_t n = (size_t)w * h * l;
+    float *g = (float *)malloc(sizeof(float) * (size_t)(2 * L + 1));
+    float *K = (float *)malloc(sizeof(float) * n);
+    if (!g || !K) { free(g); free(K); return -1; }
+    oracle_gauss_taps(sigma, L, g);
+    for (int z = 0; z < l; ++z)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const uint8_t *row = I + ((size_t)z * h + y) * w;
+                float acc = 0.0f;
+                for (int k = -L; k <= L; ++k) {
+                    int xs = x + k < 0 ? 0 : (x + k > w - 1 ? w - 1 : x + k);
+                    acc += (float)(int)row[xs] * g[k + L];
+                }
+                K[((size_t)z * h + y) * w + x] = acc;
+            }
+    for (int z = 0; z < l; ++z)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const float *pl = K + (size_t)z * h * w;
+                uint8_t acc = 0;
+                for (int k = -L; k <= L; ++k) {
+                    int ys = y + k < 0 ? 0 : (y + k > h - 1 ? h - 1 : y + k);
+                    acc = (uint8_t)((float)(int)acc + pl[(size_t)ys * w + x] * g[k + L]);
+                }
+                I[((size_t)z * h + y) * w + x] = acc;
+            }
+    free(g); free(K);
+    return 0;
+}

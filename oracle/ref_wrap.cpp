@@ -117,6 +117,14 @@ void ref_hessian2d(unsigned char* I, int w, int h, float sig, float* Dyy, float*
     f.hessian2d(I, w, h, sig, Dyy, Dxy, Dxx);
 }
 
+// The soma helpers: Frangi::imerode (frangi.h:47), Frangi::imdilate (frangi.h:49), in-place xy Frangi::imgaussian (frangi.h:43)
+__attribute__((visibility("default")))
+void ref_imerode(unsigned char* I, int w, int h, int l, float rad, unsigned char* E) { QuietCout q; Frangi::imerode(I, w, h, l, rad, E); }
+__attribute__((visibility("default")))
+void ref_imdilate(unsigned char* I, int w, int h, int l, float rad) { QuietCout q; Frangi::imdilate(I, w, h, l, rad); }
+__attribute__((visibility("default")))
+void ref_imgaussian_xy(unsigned char* I, int w, int h, int l, float sig) { QuietCout q; Frangi::imgaussian(I, w, h, l, sig); }
+
 // Seeds are returned as rows of 6 floats (x, y, z, vx, vy, vz).  Returns the
 // number of seeds found; at most `cap` rows are written.
 __attribute__((visibility("default")))

@@ -8,10 +8,10 @@
 // Same public field names, constructor and member signatures as the reference for
 // everything ON the path (frangi.h:8-24,33,35,42); every call forwards to the C-ABI
 // of include/frangi_gpu.h.  The 2-D pair frangi2d / hessian2d (frangi.h:38,40) is
-// provided too.  Members that are off the path (the soma helpers imerode / imdilate /
-// xy-imgaussian, the direction tables, the public eigen-solver entry points) are not
-// provided here: an integrator who needs them keeps the reference's frangi.cpp under
-// another class name.
+// provided too, and so are the soma helpers imerode / imdilate / in-place xy imgaussian
+// (frangi.h:47,49,43).  Not provided: the z-scaled imerode overload (frangi.h:46, never
+// called), the direction tables and the public eigen-solver entry points (dead code in the
+// plugin).
 //
 // Error behaviour: the reference's members return void and fail only by uncaught
 // std::bad_alloc; here a failed GPU call throws std::runtime_error carrying
@@ -67,6 +67,11 @@ public:
 
     // frangi.h:42
     static void imgaussian(unsigned char* I, int w, int h, int l, float sig_, float zdist_, float* F);
+
+    // frangi.h:43,47,49 -- the soma branch (Advantra_plugin.cpp:2432,2438)
+    static void imgaussian(unsigned char* I, int w, int h, int l, float sig_);
+    static void imerode(unsigned char* I, int w, int h, int l, float rad, unsigned char* E);
+    static void imdilate(unsigned char* I, int w, int h, int l, float rad);
 
 private:
     frangi_gpu* handle_;

@@ -28,6 +28,7 @@
 #include "frangi_kernels.cuh"
 #include "seed_kernels.cuh"
 #include "frangi2d_kernels.cuh"
+#include "soma_kernels.cuh"
 #include "nccl_dyn.h"
 
 #define FRANGI_API extern "C" __attribute__((visibility("default")))
@@ -1649,4 +1650,74 @@ FRANGI_API int frangi_gpu_hessian2d(const uint8_t* I_host, int w, int h, float s
     if (!Dyy || !Dxy || !Dxx) return fail(FRANGI_GPU_EINVAL, "NULL argument");
     float* const D[3] = { Dyy, Dxy, Dxx };
     return run_2d(I_host, w, h, &sigma, 1, .5f, 15.f, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, D, device, flags);
+}
+
+// ---- f4, second part: the soma helpers (soma_kernels.cuh) -------------------------------------------------
+namespace {
+struct DevSoma {
+    uint8_t *a = nullptr, *b = nullptr;
+    float* K = nullptr;
+    ~DevSoma() { cudaFree(a); cudaFree(b); cudaFree(K); }
+};
+
+int soma_args(const void* I, int w, int h, int l, int device)
+{
+    if (!I) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    if (w < 1 || h < 1 || l < 1 || (long long)w * h > 0x7fffffffLL || h > 65535)
+        return fail(FRANGI_GPU_EINVAL, "bad volume %d x %d x %d", w, h, l);
+    RC(check_device(device));
+    CK(cudaSetDevice(device));
+    return 0;
+}
+
+template <bool IS_MIN>
+int morph(const uint8_t* I_host, int w, int h, int l, float rad, uint8_t* out_host, int device)
+{
+    RC(soma_args(I_host, w, h, l, device));
+    if (!out_host || !(rad >= 0)) return fail(FRANGI_GPU_EINVAL, "bad argument");
+    const int L = (int)std::ceil(rad);                         // frangi.cpp:885
+    const size_t n = (size_t)w * h * l;
+    DevSoma d;
+    CK(cudaMalloc(&d.a, n));
+    CK(cudaMalloc(&d.b, n));
+    CK(cudaMemcpy(d.a, I_host, n, cudaMemcpyHostToDevice));
+    const dim3 grid((w + 255) / 256, h, (unsigned)std::min(l, 4096));
+    morph_pass_kernel<IS_MIN, false><<<grid, 256>>>(d.a, d.b, w, h, l, L);
+    morph_pass_kernel<IS_MIN, true><<<grid, 256>>>(d.b, d.a, w, h, l, L);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out_host, d.a, n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+}  // namespace
+
+FRANGI_API int frangi_gpu_imerode(const uint8_t* I_host, int w, int h, int l, float rad, uint8_t* E_host, int device)
+{
+    return morph<true>(I_host, w, h, l, rad, E_host, device);
+}
+
+FRANGI_API int frangi_gpu_imdilate(uint8_t* I_host, int w, int h, int l, float rad, int device)
+{
+    return morph<false>(I_host, w, h, l, rad, I_host, device);
+}
+
+FRANGI_API int frangi_gpu_imgaussian_xy(uint8_t* I_host, int w, int h, int l, float sig, int device)
+{
+    RC(soma_args(I_host, w, h, l, device));
+    if (!(sig > 0)) return fail(FRANGI_GPU_EINVAL, "sigma must be > 0");
+    int r_true = 0, r_tmpl = 0;
+    GaussTaps taps;
+    RC(plan_taps(sig, r_true, r_tmpl, taps));                  // frangi.cpp:792-804: the same taps as every other imgaussian
+    const size_t n = (size_t)w * h * l;
+    DevSoma d;
+    CK(cudaMalloc(&d.a, n));
+    CK(cudaMalloc(&d.K, sizeof(float) * n));
+    CK(cudaMemcpy(d.a, I_host, n, cudaMemcpyHostToDevice));
+    const dim3 grid((w + 255) / 256, h, (unsigned)std::min(l, 4096));
+    gauss_x_u8_kernel<<<grid, 256>>>(d.a, d.K, w, h, l, r_true, r_tmpl, taps);
+    gauss_y_trunc_kernel<<<grid, 256>>>(d.K, d.a, w, h, l, r_true, r_tmpl, taps);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(I_host, d.a, n, cudaMemcpyDeviceToHost));
+    return 0;
 }

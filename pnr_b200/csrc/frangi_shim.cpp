@@ -95,3 +95,21 @@ void Frangi::imgaussian(unsigned char* I, int w, int h, int l, float sig_, float
     const int rc = frangi_gpu_imgaussian(I, w, h, l, sig_, zdist_, F, 0, 0);
     if (rc) raise("frangi_gpu_imgaussian", rc);
 }
+
+void Frangi::imgaussian(unsigned char* I, int w, int h, int l, float sig_)
+{
+    const int rc = frangi_gpu_imgaussian_xy(I, w, h, l, sig_, 0);
+    if (rc) raise("frangi_gpu_imgaussian_xy", rc);
+}
+
+void Frangi::imerode(unsigned char* I, int w, int h, int l, float rad, unsigned char* E)
+{
+    const int rc = frangi_gpu_imerode(I, w, h, l, rad, E, 0);
+    if (rc) raise("frangi_gpu_imerode", rc);
+}
+
+void Frangi::imdilate(unsigned char* I, int w, int h, int l, float rad)
+{
+    const int rc = frangi_gpu_imdilate(I, w, h, l, rad, 0);
+    if (rc) raise("frangi_gpu_imdilate", rc);
+}

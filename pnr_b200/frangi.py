@@ -74,6 +74,9 @@ SYMBOLS = {
     "frangi_gpu_frangi2d": (C.c_int, [_VP, C.c_int, C.c_int, _f32p, C.c_int, C.c_float, C.c_float, C.c_int, _VP, _f32p, _f32p,
                                       _VP, _VP, _VP, C.c_int, C.c_uint]),
     "frangi_gpu_hessian2d": (C.c_int, [_VP, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP, C.c_int, C.c_uint]),
+    "frangi_gpu_imerode": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, _VP, C.c_int]),
+    "frangi_gpu_imdilate": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]),
+    "frangi_gpu_imgaussian_xy": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]),
     "frangi_gpu_host_alloc": (_VP, [C.c_size_t]),
     "frangi_gpu_host_free": (None, [_VP]),
     "frangi_gpu_device_count": (C.c_int, []),
@@ -396,3 +399,27 @@ def seed_candidates(J8, device=0):
     _check(lib.frangi_gpu_seed_candidates_host(_ptr(J8), w, h, l, _ptr(lo), _ptr(hi), _ptr(n), _ptr(keys), keys.size,
                                                C.byref(total), device))
     return dict(layer_min=lo, layer_max=hi, n_max=n, keys=keys[:total.value].copy())
+
+
+def imerode(I, rad, device=0):
+    """Frangi::imerode(I,w,h,l,rad,E) (frangi.h:47): xy minimum filter of a uint8 volume [l][h][w]."""
+    I, w, h, l = _vol(I)
+    out = np.empty_like(I)
+    _check(load_library().frangi_gpu_imerode(_ptr(I), w, h, l, rad, _ptr(out), device))
+    return out
+
+
+def imdilate(I, rad, device=0):
+    """Frangi::imdilate(I,w,h,l,rad) (frangi.h:49); returns the dilated copy."""
+    I, w, h, l = _vol(I)
+    out = I.copy()
+    _check(load_library().frangi_gpu_imdilate(_ptr(out), w, h, l, rad, device))
+    return out
+
+
+def imgaussian_xy(I, sig, device=0):
+    """Frangi::imgaussian(I,w,h,l,sig) (frangi.h:43), the in-place xy Gaussian of the soma branch; returns the copy."""
+    I, w, h, l = _vol(I)
+    out = I.copy()
+    _check(load_library().frangi_gpu_imgaussian_xy(_ptr(out), w, h, l, sig, device))
+    return out

@@ -107,9 +107,20 @@ def case_e_2d():
                         J_blackwhite=Rb["J"], **{"H_" + k: v for k, v in H.items()})
 
 
+def case_f_soma():
+    """case F: the soma helpers (imerode, imdilate, in-place xy imgaussian) on a small volume."""
+    ref = Reference()
+    I = make_volume(72, 56, 8, seed=31, n_neurites=3)[2:6]
+    np.savez_compressed(os.path.join(OUT, "case_f_soma.npz"), I=I, rad=np.float32(3.0), eroded=ref.imerode(I, 3.0),
+                        dilated=ref.imdilate(I, 3.0), blurred=ref.imgaussian_xy(I, 3.0),
+                        chain=ref.imgaussian_xy(ref.imerode(I, 2.0), 2.0))      # Advantra_plugin.cpp:2432,2438
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "2d":     # only the 2-D case (leaves the other fixtures untouched)
-        case_e_2d()
-    else:
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"     # "2d" / "soma": only that case (others untouched)
+    if which in ("all",):
         main()
+    if which in ("all", "2d"):
         case_e_2d()
+    if which in ("all", "soma"):
+        case_f_soma()
