@@ -704,13 +704,14 @@ struct TileRing {
 
 // ---------------------------------------------------------------------------
 // K2 (TMA form, radius <= 12): the same register sliding window as gauss_z_march_kernel, but the
-// loads are bulk copies.  A WARP owns 64 adjacent x columns of one row and marches along z; lane 0
-// keeps DEPTH planes of the warp's 256-byte row segment in flight with cp.async.bulk.tensor on a
-// (w, h, planes) tensor map of Fxy (box 64 x 1 x 1, completion on one mbarrier per slot), every lane
-// picks its two columns out of the landed segment with one 64-bit shared load and pushes them into
-// its window.  Bytes in flight no longer depend on registers or on resident threads (DEPTH x 256 B per
-// warp), so the kernel reaches the HBM rate at every radius, and two warps with 16 KB of shared
-// memory keep 8 KB in flight -- small enough to run NEXT to a K3 CTA set on the same SM.
+// loads are bulk copies.  A WARP owns 128 adjacent x columns of one row and marches along z; lane 0
+// keeps DEPTH planes of the warp's 512-byte row segment in flight with cp.async.bulk.tensor on a
+// (w, h, planes) tensor map of Fxy (box 128 x 1 x 1, completion on one mbarrier per slot), every lane
+// picks its four columns out of the landed segment with one 128-bit shared load and pushes them into
+// its window (two independent FFMA2 chains).  Bytes in flight no longer depend on registers or on
+// resident threads (DEPTH x 512 B per warp), so the kernel runs at the HBM rate at every radius.
+// (With 64 columns per warp the per-plane bookkeeping -- barrier wait, copy issue, slot rotation --
+// made the kernel issue-bound at 80 % issue utilisation, profiles/r1m.)
 // Warps are independent (no __syncthreads): slot reuse is ordered by __syncwarp.
 // Arithmetic and accumulation order are those of gauss_z_march_kernel (bit-identical results).
 // ---------------------------------------------------------------------------
@@ -721,12 +722,12 @@ struct TileRing {
 #define ZT_WARPS 2
 #endif
 struct ZTile {
-    static constexpr int COLS = 64, DEPTH = ZT_DEPTH, WARPS = ZT_WARPS;
+    static constexpr int COLS = 128, DEPTH = ZT_DEPTH, WARPS = ZT_WARPS;   // a lane owns 4 adjacent columns
     static constexpr int SMEM_BYTES = WARPS * DEPTH * (COLS * 4 + 8);
 };
 
 template <int LZ, bool EXACT>
-__global__ void __launch_bounds__(32 * ZTile::WARPS)
+__global__ void __launch_bounds__(32 * ZTile::WARPS, 16 / ZTile::WARPS)      // up to 128 registers: no spills at radius 9, 12
 gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ ZParams p, const __grid_constant__ GaussTaps taps)
 {
     constexpr int Q = 2 * LZ + 1, D = ZTile::DEPTH;
@@ -738,7 +739,7 @@ gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     const int y = (int)(rest % p.h);
     const int zc = (int)(rest / p.h);
     if (zc >= p.nzc) return;                                   // warp-uniform
-    const int x0 = xs * ZTile::COLS, x = x0 + 2 * lane;
+    const int x0 = xs * ZTile::COLS, x = x0 + 4 * lane;
     const int t_begin = zc * p.zchunk;
     const int nout = min(p.zchunk, p.out_count - t_begin);
     const int zg0 = p.out_base + t_begin;
@@ -752,31 +753,32 @@ gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         mbar_init_fence();
     }
     __syncwarp();
-    int islot = 0;                                             // lane 0: slot of the next copy
-    auto issue = [&](int j) {
-        // replicate clamp at the volume ends (frangi.cpp:758,776), then into the resident planes (only reached by
-        // window entries that feed outputs beyond out_count, which are never produced)
-        const int zs = clampi(clampi(zg0 - LZ + j, 0, p.l - 1), p.in_base, p.in_base + p.in_count - 1) - p.tm_base;
-        mbar_expect_tx(bar_s + 8 * islot, ZTile::COLS * 4);
-        tma_load_3d(ring_s + islot * ZTile::COLS * 4, &tm, bar_s + 8 * islot, x0, y, zs);
-        islot = islot + 1 == D ? 0 : islot + 1;
+    // replicate clamp at the volume ends (frangi.cpp:758,776), then into the resident planes (only reached by window
+    // entries that feed outputs beyond out_count, which are never produced); as tensor-map plane coordinates
+    const int zlo = max(0, p.in_base) - p.tm_base, zhi = min(p.l - 1, p.in_base + p.in_count - 1) - p.tm_base;
+    int zj = zg0 - LZ - p.tm_base;                             // lane 0: unclamped coordinate of the next copy
+    uint32_t ibar = bar_s, idst = ring_s;                      // lane 0: barrier / destination of the next copy
+    auto issue = [&]() {
+        mbar_expect_tx(ibar, ZTile::COLS * 4);
+        tma_load_3d(idst, &tm, ibar, x0, y, min(max(zj, zlo), zhi));
+        ++zj; ibar += 8; idst += ZTile::COLS * 4;
+        if (ibar == bar_s + 8 * D) { ibar = bar_s; idst = ring_s; }
     };
     if (lane == 0)
-        for (int j = 0; j < min(D, nin); ++j) issue(j);
+        for (int j = 0; j < min(D, nin); ++j) issue();
     int slot = 0;
     uint32_t par = 0;
-    auto next = [&](int j) {                                   // input j of the chunk, this lane's two columns
+    auto next = [&](int j) {                                   // input j of the chunk, this lane's four columns
         mbar_wait(bar_s + 8 * slot, par);
-        const float2 v = *reinterpret_cast<const float2*>(ring + slot * ZTile::COLS + 2 * lane);
+        const float4 v = *reinterpret_cast<const float4*>(ring + slot * ZTile::COLS + 4 * lane);
         __syncwarp();                                          // every lane has its copy: the slot may be refilled
-        if (lane == 0 && j + D < nin) issue(j + D);
+        if (lane == 0 && j + D < nin) issue();
         if (++slot == D) { slot = 0; par ^= 1u; }
         return v;
     };
-    float2* __restrict__ dst = reinterpret_cast<float2*>(p.out + ((long long)t_begin * p.fplane + (long long)y * p.fpitch + x));
-    const long long plane2 = p.fplane / 2;
-    const bool store = x < p.w;
-    float2 win[Q];
+    float* __restrict__ dst = p.out + ((long long)t_begin * p.fplane + (long long)y * p.fpitch + x);
+    const bool store = x < p.w;                                // the row pitch is a multiple of 32 floats: the quad fits
+    float4 win[Q];
 #pragma unroll
     for (int j = 0; j < Q - 1; ++j) win[j] = next(j);
     for (int t0 = 0; t0 < nout; t0 += Q) {
@@ -785,18 +787,21 @@ gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             const int t = t0 + s;
             if (t < nout) {
                 win[(s + Q - 1) % Q] = next(t + Q - 1);
-                float2 acc = make_float2(0.0f, 0.0f);
+                float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int k = 0; k <= 2 * LZ; ++k) {
-                    const float2 v = win[(s + k) % Q];
+                    const float4 v = win[(s + k) % Q];
                     if (EXACT) {
-                        acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, taps.g[k]));
-                        acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, taps.g[k]));
+                        a0.x = __fadd_rn(a0.x, __fmul_rn(v.x, taps.g[k])); a0.y = __fadd_rn(a0.y, __fmul_rn(v.y, taps.g[k]));
+                        a1.x = __fadd_rn(a1.x, __fmul_rn(v.z, taps.g[k])); a1.y = __fadd_rn(a1.y, __fmul_rn(v.w, taps.g[k]));
                     } else {
-                        acc = __ffma2_rn(v, make_float2(taps.g[k], taps.g[k]), acc);
+                        const float2 g2 = make_float2(taps.g[k], taps.g[k]);
+                        a0 = __ffma2_rn(make_float2(v.x, v.y), g2, a0);
+                        a1 = __ffma2_rn(make_float2(v.z, v.w), g2, a1);
                     }
                 }
-                if (store) __stcs(dst + (long long)t * plane2, acc);
+                if (store) __stcs(reinterpret_cast<float4*>(dst), make_float4(a0.x, a0.y, a1.x, a1.y));
+                dst += p.fplane;
             }
         }
     }
