@@ -723,7 +723,7 @@ struct TileRing {
 #endif
 struct ZTile {
     static constexpr int COLS = 128, DEPTH = ZT_DEPTH, WARPS = ZT_WARPS;   // a lane owns 4 adjacent columns
-    static constexpr int SMEM_BYTES = WARPS * DEPTH * (COLS * 4 + 8);
+    static constexpr int SMEM_BYTES = WARPS * (DEPTH * (COLS * 4 + 8) + 128);   // rings, barriers, one scratch word per lane
 };
 
 template <int LZ, bool EXACT>
@@ -747,6 +747,7 @@ gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     const float* ring = zring + warp * D * ZTile::COLS;
     const uint32_t ring_s = smem_u32(ring);
     const uint32_t bar_s = smem_u32(zring + ZTile::WARPS * D * ZTile::COLS) + warp * D * 8;
+    const uint32_t scratch_s = smem_u32(zring + ZTile::WARPS * D * ZTile::COLS) + ZTile::WARPS * D * 8 + warp * 128 + lane * 4;
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < D; ++k) mbar_init(bar_s + 8 * k, 1);
@@ -771,7 +772,13 @@ gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     auto next = [&](int j) {                                   // input j of the chunk, this lane's four columns
         mbar_wait(bar_s + 8 * slot, par);
         const float4 v = *reinterpret_cast<const float4*>(ring + slot * ZTile::COLS + 4 * lane);
-        __syncwarp();                                          // every lane has its copy: the slot may be refilled
+        // The slot may be refilled only after the shared-memory load has DELIVERED: the load is asynchronous to the
+        // instruction stream (its result is first needed many instructions later), and a refill that is served from
+        // L2 can land while a quarter-warp of the load is still queued in the memory pipeline -- seen as rare 16-byte
+        // corruptions when NCCL kernels ran beside this one.
+        // A store of the loaded value cannot issue before the load has delivered and stays ahead of the copy below.
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch_s), "f"(v.w) : "memory");
+        __syncwarp();                                          // every lane has its copy
         if (lane == 0 && j + D < nin) issue();
         if (++slot == D) { slot = 0; par ^= 1u; }
         return v;
