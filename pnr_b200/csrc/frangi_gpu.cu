@@ -206,6 +206,22 @@ int launch_z_e(int L, const ZParams& p, const GaussTaps& t, long long nblocks, c
     return fail(FRANGI_GPU_EINVAL, "no gauss_z instantiation for radius %d", L);
 }
 
+// Device scratch of the pre-pass, kept between calls (allocation and release are synchronising and slow next to the
+// kernels): per-layer ranges / counters / offsets, the two key arrays of the sort and its temporary storage.
+struct SeedScratch {
+    int *minmax = nullptr, *count = nullptr;
+    long long *off = nullptr, *in = nullptr, *out = nullptr;
+    void* tmp = nullptr;
+    int layers = 0;
+    long long keys = 0;
+    size_t tmp_bytes = 0;
+    void release()
+    {
+        cudaFree(minmax); cudaFree(count); cudaFree(off); cudaFree(in); cudaFree(out); cudaFree(tmp);
+        *this = SeedScratch();
+    }
+};
+
 // ---- one z-slab on one device -----------------------------------------------
 struct Slab {
     int dev = 0;
@@ -229,6 +245,7 @@ struct Slab {
     CUtensorMap tmFB{}, tmFcB{}, tmFxyB{};
     cudaStream_t s_aux = nullptr;
     std::vector<cudaEvent_t> ev_ov;
+    SeedScratch seed;               // scratch of frangi_gpu_seed_candidates
     bool has_tm = false;
     int* dMinMax = nullptr;
     int* hMinMax = nullptr;   // pinned
@@ -273,6 +290,7 @@ void free_slab(Slab& s)
     cudaFree(s.dI); cudaFree(s.dFxy); cudaFree(s.dF); cudaFree(s.dJ);
     cudaFree(s.dVx); cudaFree(s.dVy); cudaFree(s.dVz); cudaFree(s.dScale); cudaFree(s.dJ8);
     cudaFree(s.dDir); cudaFree(s.dMinMax);
+    s.seed.release();
     if (s.hMinMax) cudaFreeHost(s.hMinMax);
     for (auto e : s.ev_all) cudaEventDestroy(e);
     if (s.ev_boundary) cudaEventDestroy(s.ev_boundary);
@@ -1469,35 +1487,35 @@ namespace {
 
 // The pre-pass on `nl` layers of a dense device J8 volume; host outputs (layer_min/max/n_max per layer,
 // keys appended at keys[*n_keys ...]).  keys == NULL or a too small keys_cap only counts.
-int seed_candidates_device(const uint8_t* dJ8, int w, int h, int nl, cudaStream_t st, uint8_t* layer_min,
+int seed_candidates_device(SeedScratch& sc, const uint8_t* dJ8, int w, int h, int nl, cudaStream_t st, uint8_t* layer_min,
                            uint8_t* layer_max, int* n_max, int64_t* keys, int64_t keys_cap, int64_t* n_keys)
 {
     if (nl < 1) return 0;
     if (nl > 65535) return fail(FRANGI_GPU_EINVAL, "seed_candidates: more than 65535 layers on one device");
     const long long plane = (long long)w * h;
-    int *d_minmax = nullptr, *d_count = nullptr;
-    long long *d_off = nullptr, *d_in = nullptr, *d_out = nullptr;
-    void* d_tmp = nullptr;
-    auto cleanup = [&]() { cudaFree(d_minmax); cudaFree(d_count); cudaFree(d_off); cudaFree(d_in); cudaFree(d_out); cudaFree(d_tmp); };
-#define CKS(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return fail(FRANGI_GPU_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+    if (sc.layers < nl) {
+        cudaFree(sc.minmax); cudaFree(sc.count); cudaFree(sc.off);
+        sc.minmax = sc.count = nullptr; sc.off = nullptr; sc.layers = 0;
+        CK(cudaMalloc(&sc.minmax, sizeof(int) * 2 * nl));
+        CK(cudaMalloc(&sc.count, sizeof(int) * nl));
+        CK(cudaMalloc(&sc.off, sizeof(long long) * (nl + 1)));
+        sc.layers = nl;
+    }
     std::vector<int> h_minmax(2 * (size_t)nl), h_count(nl);
     for (int z = 0; z < nl; ++z) { h_minmax[2 * z] = 255; h_minmax[2 * z + 1] = 0; }
-    CKS(cudaMalloc(&d_minmax, sizeof(int) * 2 * nl));
-    CKS(cudaMalloc(&d_count, sizeof(int) * nl));
-    CKS(cudaMalloc(&d_off, sizeof(long long) * (nl + 1)));
-    CKS(cudaMemcpyAsync(d_minmax, h_minmax.data(), sizeof(int) * 2 * nl, cudaMemcpyHostToDevice, st));
-    CKS(cudaMemsetAsync(d_count, 0, sizeof(int) * nl, st));
+    CK(cudaMemcpyAsync(sc.minmax, h_minmax.data(), sizeof(int) * 2 * nl, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(sc.count, 0, sizeof(int) * nl, st));
     const int nb = (int)std::min<long long>(std::max<long long>(1, plane / (4 * 256 * 8)), 148 * 8);
-    j8_layer_minmax_kernel<<<dim3(nb, nl), 256, 0, st>>>(dJ8, plane, d_minmax);
+    j8_layer_minmax_kernel<<<dim3(nb, nl), 256, 0, st>>>(dJ8, plane, sc.minmax);
     g_launches++;
     const dim3 grid((w + 31) / 32, (h + 7) / 8, nl), block(32, 8);
-    if (grid.y > 65535) { cleanup(); return fail(FRANGI_GPU_EINVAL, "seed_candidates: layer too tall"); }
-    j8_local_maxima_kernel<false><<<grid, block, 0, st>>>(dJ8, w, h, d_minmax, d_count, nullptr, nullptr);
+    if (grid.y > 65535) return fail(FRANGI_GPU_EINVAL, "seed_candidates: layer too tall");
+    j8_local_maxima_kernel<false><<<grid, block, 0, st>>>(dJ8, w, h, sc.minmax, sc.count, nullptr, nullptr);
     g_launches++;
-    CKS(cudaGetLastError());
-    CKS(cudaMemcpyAsync(h_count.data(), d_count, sizeof(int) * nl, cudaMemcpyDeviceToHost, st));
-    CKS(cudaMemcpyAsync(h_minmax.data(), d_minmax, sizeof(int) * 2 * nl, cudaMemcpyDeviceToHost, st));
-    CKS(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_count.data(), sc.count, sizeof(int) * nl, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_minmax.data(), sc.minmax, sizeof(int) * 2 * nl, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     std::vector<long long> h_off(nl + 1, 0);
     for (int z = 0; z < nl; ++z) {
         h_off[z + 1] = h_off[z] + h_count[z];
@@ -1507,23 +1525,30 @@ int seed_candidates_device(const uint8_t* dJ8, int w, int h, int nl, cudaStream_
     const long long total = h_off[nl];
     const int64_t at = *n_keys;
     *n_keys = at + total;
-    if (!keys || at + total > keys_cap || total == 0) { cleanup(); return 0; }   // counted only (the caller checks n_keys against its capacity)
-    CKS(cudaMalloc(&d_in, sizeof(long long) * total));
-    CKS(cudaMalloc(&d_out, sizeof(long long) * total));
-    CKS(cudaMemcpyAsync(d_off, h_off.data(), sizeof(long long) * (nl + 1), cudaMemcpyHostToDevice, st));
-    CKS(cudaMemsetAsync(d_count, 0, sizeof(int) * nl, st));
-    j8_local_maxima_kernel<true><<<grid, block, 0, st>>>(dJ8, w, h, d_minmax, d_count, d_off, d_in);
+    if (!keys || at + total > keys_cap || total == 0) return 0;   // counted only (the caller checks n_keys against its capacity)
+    if (sc.keys < total) {
+        cudaFree(sc.in); cudaFree(sc.out);
+        sc.in = sc.out = nullptr; sc.keys = 0;
+        CK(cudaMalloc(&sc.in, sizeof(long long) * total));
+        CK(cudaMalloc(&sc.out, sizeof(long long) * total));
+        sc.keys = total;
+    }
+    CK(cudaMemcpyAsync(sc.off, h_off.data(), sizeof(long long) * (nl + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(sc.count, 0, sizeof(int) * nl, st));
+    j8_local_maxima_kernel<true><<<grid, block, 0, st>>>(dJ8, w, h, sc.minmax, sc.count, sc.off, sc.in);
     g_launches++;
-    CKS(cudaGetLastError());
+    CK(cudaGetLastError());
     size_t tmp_bytes = 0;
-    CKS(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, d_in, d_out, total, nl, d_off, d_off + 1, 0, 63, st));
-    CKS(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
-    CKS(cub::DeviceSegmentedRadixSort::SortKeys(d_tmp, tmp_bytes, d_in, d_out, total, nl, d_off, d_off + 1, 0, 63, st));
+    CK(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, sc.in, sc.out, total, nl, sc.off, sc.off + 1, 0, 63, st));
+    if (sc.tmp_bytes < tmp_bytes) {
+        cudaFree(sc.tmp); sc.tmp = nullptr; sc.tmp_bytes = 0;
+        CK(cudaMalloc(&sc.tmp, std::max<size_t>(tmp_bytes, 16)));
+        sc.tmp_bytes = std::max<size_t>(tmp_bytes, 16);
+    }
+    CK(cub::DeviceSegmentedRadixSort::SortKeys(sc.tmp, tmp_bytes, sc.in, sc.out, total, nl, sc.off, sc.off + 1, 0, 63, st));
     g_launches++;
-    CKS(cudaMemcpyAsync(keys + at, d_out, sizeof(long long) * total, cudaMemcpyDeviceToHost, st));
-    CKS(cudaStreamSynchronize(st));
-#undef CKS
-    cleanup();
+    CK(cudaMemcpyAsync(keys + at, sc.out, sizeof(long long) * total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -1539,8 +1564,8 @@ FRANGI_API int frangi_gpu_seed_candidates(frangi_gpu_t* H, uint8_t* layer_min, u
     for (auto& s : H->slabs) {       // layers are independent: every slab handles its own, in z order
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamSynchronize(s.s_main));
-        RC(seed_candidates_device(s.dJ8, H->w, H->h, s.ze - s.zb, s.s_main, layer_min + zoff, layer_max + zoff, n_max + zoff,
-                                  keys, keys_cap, n_keys));
+        RC(seed_candidates_device(s.seed, s.dJ8, H->w, H->h, s.ze - s.zb, s.s_main, layer_min + zoff,
+                                  layer_max + zoff, n_max + zoff, keys, keys_cap, n_keys));
         zoff += s.ze - s.zb;
     }
     if (keys && *n_keys > keys_cap) return fail(FRANGI_GPU_EINVAL, "seed_candidates: %lld keys, capacity %lld", (long long)*n_keys, (long long)keys_cap);
@@ -1561,9 +1586,11 @@ FRANGI_API int frangi_gpu_seed_candidates_host(const uint8_t* J8_host, int w, in
     if (e != cudaSuccess) { cudaFree(d); return fail(FRANGI_GPU_ECUDA, "upload failed: %s", cudaGetErrorString(e)); }
     *n_keys = 0;
     int rc = 0;
+    SeedScratch sc;
     for (int z0 = 0; z0 < l && rc == 0; z0 += 65535)
-        rc = seed_candidates_device(d + (size_t)z0 * w * h, w, h, std::min(65535, l - z0), 0, layer_min + z0, layer_max + z0, n_max + z0,
-                                    keys, keys_cap, n_keys);
+        rc = seed_candidates_device(sc, d + (size_t)z0 * w * h, w, h, std::min(65535, l - z0), 0, layer_min + z0, layer_max + z0,
+                                    n_max + z0, keys, keys_cap, n_keys);
+    sc.release();
     cudaFree(d);
     if (rc) return rc;
     if (keys && *n_keys > keys_cap) return fail(FRANGI_GPU_EINVAL, "seed_candidates: %lld keys, capacity %lld", (long long)*n_keys, (long long)keys_cap);
