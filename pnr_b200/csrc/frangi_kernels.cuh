@@ -533,89 +533,6 @@ gauss_z_march_kernel(const __grid_constant__ ZParams p, const __grid_constant__ 
     }
 }
 
-// ---------------------------------------------------------------------------
-// Second differences with the reference's face rules (frangi.cpp:306-381):
-// first difference along an axis = s * (f[hi] - f[lo]) with lo = max(c-1,0),
-// hi = min(c+1,n-1), s = 1 on a face and 0.5 inside; the second difference
-// applies the same rule to the first-difference field; then * sigma^2.
-// Coordinates are GLOBAL (slab faces are not volume faces).
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ float face_scale(int c, int n) { return (c == 0 || c == n - 1) ? 1.0f : 0.5f; }
-
-struct Hess { float xx, xy, xz, yy, yz, zz; };
-
-// Generic form for voxels within two steps of a volume face.  `Field` provides
-// at(x, y, z) for any coordinate inside the volume and within +-2 of the voxel.
-template <class Field>
-__device__ __forceinline__ float d_dx(const Field& f, int x, int y, int z)
-{
-    return __fmul_rn(face_scale(x, f.w), __fsub_rn(f.at(min(x + 1, f.w - 1), y, z), f.at(max(x - 1, 0), y, z)));
-}
-template <class Field>
-__device__ __forceinline__ float d_dy(const Field& f, int x, int y, int z)
-{
-    return __fmul_rn(face_scale(y, f.h), __fsub_rn(f.at(x, min(y + 1, f.h - 1), z), f.at(x, max(y - 1, 0), z)));
-}
-template <class Field>
-__device__ __forceinline__ float d_dz(const Field& f, int x, int y, int z)
-{
-    return __fmul_rn(face_scale(z, f.l), __fsub_rn(f.at(x, y, min(z + 1, f.l - 1)), f.at(x, y, max(z - 1, 0))));
-}
-
-template <class Field>
-__device__ __noinline__ Hess hessian_at_face(const Field& f, int x, int y, int z, float sigma2)
-{
-    const int xl = max(x - 1, 0), xh = min(x + 1, f.w - 1);
-    const int yl = max(y - 1, 0), yh = min(y + 1, f.h - 1);
-    const int zl = max(z - 1, 0), zh = min(z + 1, f.l - 1);
-    const float sx = face_scale(x, f.w), sy = face_scale(y, f.h), sz = face_scale(z, f.l);
-    Hess H;
-    H.xx = __fmul_rn(__fmul_rn(sx, __fsub_rn(d_dx(f, xh, y, z), d_dx(f, xl, y, z))), sigma2);
-    H.xy = __fmul_rn(__fmul_rn(sy, __fsub_rn(d_dx(f, x, yh, z), d_dx(f, x, yl, z))), sigma2);
-    H.xz = __fmul_rn(__fmul_rn(sz, __fsub_rn(d_dx(f, x, y, zh), d_dx(f, x, y, zl))), sigma2);
-    H.yy = __fmul_rn(__fmul_rn(sy, __fsub_rn(d_dy(f, x, yh, z), d_dy(f, x, yl, z))), sigma2);
-    H.yz = __fmul_rn(__fmul_rn(sz, __fsub_rn(d_dy(f, x, y, zh), d_dy(f, x, y, zl))), sigma2);
-    H.zz = __fmul_rn(__fmul_rn(sz, __fsub_rn(d_dz(f, x, y, zh), d_dz(f, x, y, zl))), sigma2);
-    return H;
-}
-
-// ---------------------------------------------------------------------------
-// K3: Hessian -> eigen -> vesselness -> running max over scales.
-//
-// Two kernels per scale share the per-voxel stage:
-//
-// K3a hessian_eigen_kernel (interior, > 98 % of the voxels of a real volume):
-// a CTA owns a 128 x 16 column of voxels and marches along z through its chunk.
-// The five planes z-2 .. z+2 of the smoothed volume F that the twice-applied
-// central difference touches live in a six-slot shared-memory ring of
-// (16+4) x (128+4) tiles (slot = plane mod 6, so the plane being staged never
-// aliases one being read and one __syncthreads per plane suffices).  The next
-// plane's tile is copied global -> shared with cp.async (LDGSTS, 8-byte units,
-// no staging registers) while the current plane is processed.  A thread produces 4 consecutive x voxels
-// of 2 rows per plane: window rows are read with 128-bit / 64-bit shared loads
-// (6.5 loads per voxel) and results leave as float4 / uchar4 stores.  Voxels at
-// least two steps from every volume face take the closed interior form,
-// bit-identical to the reference's two-pass form:
-//   Dxx = ((F[x+2]-F[x]) - (F[x]-F[x-2])) * (sigma^2/4),
-//   Dxy = ((F[+1,+1]-F[-1,+1]) - (F[+1,-1]-F[-1,-1])) * (sigma^2/4)
-// (halving is exact, so the 0.5 factors commute with the roundings of
-// frangi.cpp:308-381).  The kernel never touches a voxel within two steps of a
-// volume face.
-//
-// K3b hessian_eigen_shell_kernel: the two-voxel-thick shell next to the volume
-// faces (x, y < 2 or > n-3; z likewise), one thread per voxel, generic face
-// rules straight from global memory.  Runs after K3a on the same stream.
-//
-// Outputs are dense over the slab's own planes [z_begin, z_begin + nz).
-// MODE 0: first scale, store unconditionally (frangi.cpp:234-252);
-// MODE 1: later scale, overwrite only on a strictly greater response (:254-271);
-//         BRIGHT = true adds the shortcut ordering for bright ridges (frangi_voxel_math.cuh);
-// MODE 2: stage dump of the six second differences (hessian3d parity).
-// minmax[0] = bits of min J (taken on the first scale, see DESIGN.md),
-// minmax[1] = bits of max J (max over every value any scale leaves in J).  J >= 0, so the int
-// order of the bit patterns is the float order.
-// ---------------------------------------------------------------------------
-
 // ---- TMA tile staging (cp.async.bulk.tensor + mbarrier) ----------------------------------------
 // The K3 kernels stage one (PW x PH x 1) box of the smoothed volume F per plane with a single
 // instruction issued by one thread; the copy engine zero-fills whatever lies outside the tensor
@@ -813,6 +730,91 @@ gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         }
     }
 }
+
+
+// ---------------------------------------------------------------------------
+// Second differences with the reference's face rules (frangi.cpp:306-381):
+// first difference along an axis = s * (f[hi] - f[lo]) with lo = max(c-1,0),
+// hi = min(c+1,n-1), s = 1 on a face and 0.5 inside; the second difference
+// applies the same rule to the first-difference field; then * sigma^2.
+// Coordinates are GLOBAL (slab faces are not volume faces).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float face_scale(int c, int n) { return (c == 0 || c == n - 1) ? 1.0f : 0.5f; }
+
+struct Hess { float xx, xy, xz, yy, yz, zz; };
+
+// Generic form for voxels within two steps of a volume face.  `Field` provides
+// at(x, y, z) for any coordinate inside the volume and within +-2 of the voxel.
+template <class Field>
+__device__ __forceinline__ float d_dx(const Field& f, int x, int y, int z)
+{
+    return __fmul_rn(face_scale(x, f.w), __fsub_rn(f.at(min(x + 1, f.w - 1), y, z), f.at(max(x - 1, 0), y, z)));
+}
+template <class Field>
+__device__ __forceinline__ float d_dy(const Field& f, int x, int y, int z)
+{
+    return __fmul_rn(face_scale(y, f.h), __fsub_rn(f.at(x, min(y + 1, f.h - 1), z), f.at(x, max(y - 1, 0), z)));
+}
+template <class Field>
+__device__ __forceinline__ float d_dz(const Field& f, int x, int y, int z)
+{
+    return __fmul_rn(face_scale(z, f.l), __fsub_rn(f.at(x, y, min(z + 1, f.l - 1)), f.at(x, y, max(z - 1, 0))));
+}
+
+template <class Field>
+__device__ __noinline__ Hess hessian_at_face(const Field& f, int x, int y, int z, float sigma2)
+{
+    const int xl = max(x - 1, 0), xh = min(x + 1, f.w - 1);
+    const int yl = max(y - 1, 0), yh = min(y + 1, f.h - 1);
+    const int zl = max(z - 1, 0), zh = min(z + 1, f.l - 1);
+    const float sx = face_scale(x, f.w), sy = face_scale(y, f.h), sz = face_scale(z, f.l);
+    Hess H;
+    H.xx = __fmul_rn(__fmul_rn(sx, __fsub_rn(d_dx(f, xh, y, z), d_dx(f, xl, y, z))), sigma2);
+    H.xy = __fmul_rn(__fmul_rn(sy, __fsub_rn(d_dx(f, x, yh, z), d_dx(f, x, yl, z))), sigma2);
+    H.xz = __fmul_rn(__fmul_rn(sz, __fsub_rn(d_dx(f, x, y, zh), d_dx(f, x, y, zl))), sigma2);
+    H.yy = __fmul_rn(__fmul_rn(sy, __fsub_rn(d_dy(f, x, yh, z), d_dy(f, x, yl, z))), sigma2);
+    H.yz = __fmul_rn(__fmul_rn(sz, __fsub_rn(d_dy(f, x, y, zh), d_dy(f, x, y, zl))), sigma2);
+    H.zz = __fmul_rn(__fmul_rn(sz, __fsub_rn(d_dz(f, x, y, zh), d_dz(f, x, y, zl))), sigma2);
+    return H;
+}
+
+// ---------------------------------------------------------------------------
+// K3: Hessian -> eigen -> vesselness -> running max over scales.
+//
+// Two kernels per scale share the per-voxel stage:
+//
+// K3a hessian_eigen_kernel (interior, > 98 % of the voxels of a real volume):
+// a CTA owns a 128 x 16 column of voxels and marches along z through its chunk.
+// The five planes z-2 .. z+2 of the smoothed volume F that the twice-applied
+// central difference touches live in a six-slot shared-memory ring of
+// (16+4) x (128+4) tiles (TileRing: the plane being staged never aliases one
+// being read and one __syncthreads per plane suffices).  The next plane's tile
+// is copied global -> shared by TMA (one cp.async.bulk.tensor of thread 0, completion
+// on the slot's mbarrier) while the current plane is processed.  A thread produces 4
+// consecutive x voxels of 2 rows per plane: window rows are read with 128-bit /
+// 64-bit shared loads (6.5 loads per voxel) and results leave as two 64-bit pairs
+// (tiles start at x = 2, see the kernel).  Voxels at
+// least two steps from every volume face take the closed interior form,
+// bit-identical to the reference's two-pass form:
+//   Dxx = ((F[x+2]-F[x]) - (F[x]-F[x-2])) * (sigma^2/4),
+//   Dxy = ((F[+1,+1]-F[-1,+1]) - (F[+1,-1]-F[-1,-1])) * (sigma^2/4)
+// (halving is exact, so the 0.5 factors commute with the roundings of
+// frangi.cpp:308-381).  The kernel never touches a voxel within two steps of a
+// volume face.
+//
+// K3b hessian_eigen_shell_kernel: the two-voxel-thick shell next to the volume
+// faces (x, y < 2 or > n-3; z likewise), one thread per voxel, generic face
+// rules straight from global memory.  Runs after K3a on the same stream.
+//
+// Outputs are dense over the slab's own planes [z_begin, z_begin + nz).
+// MODE 0: first scale, store unconditionally (frangi.cpp:234-252);
+// MODE 1: later scale, overwrite only on a strictly greater response (:254-271);
+//         BRIGHT = true adds the shortcut ordering for bright ridges (frangi_voxel_math.cuh);
+// MODE 2: stage dump of the six second differences (hessian3d parity).
+// minmax[0] = bits of min J (taken on the first scale, see DESIGN.md),
+// minmax[1] = bits of max J (max over every value any scale leaves in J).  J >= 0, so the int
+// order of the bit patterns is the float order.
+// ---------------------------------------------------------------------------
 
 struct FView {
     const float* F;     // plane 0 = global plane base
