@@ -406,9 +406,13 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     CK(cudaMalloc(&s.dF, sizeof(float) * (size_t)H->fplane * (s.fe - s.fb)));
     RC(make_tile_map(&s.tmFxy, s.dFxy, H->w, H->h, s.xe - s.xb, H->fpitch, H->fplane, ZTile::COLS, 1));
     s.dFxy0 = s.dFxy;
+    // finite from the start: a z pass whose template radius exceeds the true one reads a few planes with zero taps,
+    // possibly halo planes that have not arrived yet (0 x finite = 0; never 0 x garbage)
+    CK(cudaMemset(s.dFxy, 0, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
     if (H->overlap) {
         CK(cudaMalloc(&s.dFxyB, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
         CK(cudaMalloc(&s.dFB, sizeof(float) * (size_t)H->fplane * (s.fe - s.fb)));
+        CK(cudaMemset(s.dFxyB, 0, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
         RC(make_tile_map(&s.tmFxyB, s.dFxyB, H->w, H->h, s.xe - s.xb, H->fpitch, H->fplane, ZTile::COLS, 1));
         RC(make_tile_map(&s.tmFB, s.dFB, H->w, H->h, s.fe - s.fb, H->fpitch, H->fplane, HessTile::PW, HessTile::PH));
         RC(make_tile_map(&s.tmFcB, s.dFB, H->w, H->h, s.fe - s.fb, H->fpitch, H->fplane, HessTileC::PW, HessTileC::PH));
@@ -514,14 +518,17 @@ int launch_zm_e(int L, const ZParams& p, const GaussTaps& t, long long nblocks, 
     return fail(FRANGI_GPU_EINVAL, "no marching gauss_z instantiation for radius %d", L);
 }
 
-int launch_z(frangi_gpu* H, Slab& s, const ScalePlan& sp, cudaStream_t stream = nullptr)
+// z smoothing of the F planes [f0, f1) of slab s (default: all of [s.fb, s.fe)); plane p lands at plane p - s.fb of s.dF
+int launch_z(frangi_gpu* H, Slab& s, const ScalePlan& sp, cudaStream_t stream = nullptr, int f0 = -1, int f1 = -1)
 {
+    if (f0 < 0) { f0 = s.fb; f1 = s.fe; }
+    if (f1 <= f0) return 0;
     ZParams p;
-    p.in = s.dFxy; p.out = s.dF;
+    p.in = s.dFxy; p.out = s.dF + (size_t)(f0 - s.fb) * H->fplane;
     p.w = H->w; p.h = H->h; p.l = H->l;
     p.fpitch = H->fpitch; p.fplane = H->fplane;
     p.in_base = s.xb; p.in_count = s.xe - s.xb;
-    p.out_base = s.fb; p.out_count = s.fe - s.fb;
+    p.out_base = f0; p.out_count = f1 - f0;
     const bool fma = (H->flags & FRANGI_GPU_FLAG_FMA_SMOOTHING) != 0;
     cudaStream_t st = stream ? stream : s.s_main;
     if (Z_TMA && sp.rz_t <= 12) {
@@ -676,23 +683,6 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
 // neighbours.  Slab k sends its lowest `halo` own planes down and its highest
 // `halo` own planes up, and receives the matching planes into the halo regions
 // of its Fxy buffer.  All calls of all local slabs sit in one NCCL group.
-// A view of planes [cz0, cz1) of a slab for the z pass and the Hessian / eigen stage: same
-// buffers, outputs offset to the view's first plane, F and Fxy ranges clipped to what the slab
-// holds (own planes plus exchanged halo).  The xy-smoothed planes keep the slab's layout.
-Slab slab_view(frangi_gpu* H, const Slab& s, int cz0, int cz1)
-{
-    Slab v = s;
-    v.zb = cz0; v.ze = cz1;
-    v.fb = std::max(cz0 - 2, s.fb); v.fe = std::min(cz1 + 2, s.fe);
-    v.xb = std::max(v.fb - H->rz_max, s.xb); v.xe = std::min(v.fe + H->rz_max, s.xe);
-    v.dFxy = s.dFxy + (size_t)(v.xb - s.xb) * H->fplane;
-    const size_t off = (size_t)(cz0 - s.zb) * H->w * H->h;
-    v.dJ = s.dJ + off; v.dVx = s.dVx + off; v.dVy = s.dVy + off; v.dVz = s.dVz + off;
-    if (s.dScale) v.dScale = s.dScale + off;
-    if (s.dDir) v.dDir = s.dDir + off;
-    return v;
-}
-
 // Local-copy form (every slab lives in this process; used when device ids repeat or
 // FRANGI_GPU_FLAG_LOCAL_HALO is set): each slab PULLS its halo planes from its neighbours'
 // boundary planes with peer copies on its comm stream, after both its own and the
@@ -771,64 +761,63 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
         CK(cudaMemcpyAsync(s.dMinMax, s.hMinMax, 2 * sizeof(int), cudaMemcpyHostToDevice, s.s_main));
         CK(cudaEventRecord(s.ev_time[0], s.s_main));
     }
-    for (int si = 0; si < S; ++si) {
+    // Multi-slab: the xy pass of a scale on every local slab -- boundary planes first, then the halo exchange on the
+    // comm streams, then the interior planes while the exchange is in flight.
+    auto xy_and_exchange = [&](int si) -> int {
         const ScalePlan& sp = H->scales[si];
         const int halo = sp.rz + 2;
-        if (multi) {
-            // boundary planes first, so that the exchange overlaps the interior
-            for (size_t k = 0; k < H->slabs.size(); ++k) {
-                Slab& s = H->slabs[k];
-                CK(cudaSetDevice(s.dev));
-                if (H->local_halo && si > 0) {   // neighbours have pulled the previous scale's boundary planes
-                    if (k > 0) CK(cudaStreamWaitEvent(s.s_main, H->slabs[k - 1].ev_halo, 0));
-                    if (k + 1 < H->slabs.size()) CK(cudaStreamWaitEvent(s.s_main, H->slabs[k + 1].ev_halo, 0));
-                }
-                const int nz = s.ze - s.zb;
-                if (nz <= 2 * halo) {
-                    RC(launch_xy(H, s, sp, I_own[k], s.zb, s.ze));
-                } else {
-                    RC(launch_xy(H, s, sp, I_own[k], s.zb, s.zb + halo));
-                    RC(launch_xy(H, s, sp, I_own[k], s.ze - halo, s.ze));
-                }
-                CK(cudaEventRecord(s.ev_boundary, s.s_main));
-                CK(cudaStreamWaitEvent(s.s_comm, s.ev_boundary, 0));
+        for (size_t k = 0; k < H->slabs.size(); ++k) {
+            Slab& s = H->slabs[k];
+            CK(cudaSetDevice(s.dev));
+            if (H->local_halo && si > 0) {   // neighbours have pulled the previous scale's boundary planes
+                if (k > 0) CK(cudaStreamWaitEvent(s.s_main, H->slabs[k - 1].ev_halo, 0));
+                if (k + 1 < H->slabs.size()) CK(cudaStreamWaitEvent(s.s_main, H->slabs[k + 1].ev_halo, 0));
             }
-            RC(exchange_halos(H, halo));
-            for (size_t k = 0; k < H->slabs.size(); ++k) {
-                Slab& s = H->slabs[k];
+            const int nz = s.ze - s.zb;
+            if (nz <= 2 * halo) {
+                RC(launch_xy(H, s, sp, I_own[k], s.zb, s.ze));
+            } else {
+                RC(launch_xy(H, s, sp, I_own[k], s.zb, s.zb + halo));
+                RC(launch_xy(H, s, sp, I_own[k], s.ze - halo, s.ze));
+            }
+            CK(cudaEventRecord(s.ev_boundary, s.s_main));
+            CK(cudaStreamWaitEvent(s.s_comm, s.ev_boundary, 0));
+        }
+        RC(exchange_halos(H, halo));
+        for (size_t k = 0; k < H->slabs.size(); ++k) {
+            Slab& s = H->slabs[k];
+            CK(cudaSetDevice(s.dev));
+            CK(cudaEventRecord(s.ev_halo, s.s_comm));
+            const int nz = s.ze - s.zb;
+            if (nz > 2 * halo) RC(launch_xy(H, s, sp, I_own[k], s.zb + halo, s.ze - halo));
+        }
+        return 0;
+    };
+    for (int si = 0; si < S; ++si) {
+        const ScalePlan& sp = H->scales[si];
+        if (multi) {
+            // Scales are software-pipelined so that a halo exchange never waits in the open: the xy pass and the
+            // exchange of scale si+1 are issued BEFORE the Hessian / eigen stage of scale si (which reads neither Fxy
+            // nor the halo), so the exchange has that whole stage to finish.  Per scale and slab: wait for the halo,
+            // ONE z pass over all F planes, [xy pass + exchange of the next scale], ONE Hessian / eigen launch -- no
+            // plane is smoothed or staged twice.  The single Fxy / F buffers are safe: the next xy pass follows this
+            // scale's z pass on the same stream, and the next z pass follows this scale's Hessian / eigen stage.
+            if (si == 0) RC(xy_and_exchange(0));
+            for (auto& s : H->slabs) {
                 CK(cudaSetDevice(s.dev));
                 cudaEvent_t* ev = s.ev_time + kEvPerScale * si;
-                CK(cudaEventRecord(s.ev_halo, s.s_comm));
-                const int nz = s.ze - s.zb;
-                if (nz > 2 * halo) RC(launch_xy(H, s, sp, I_own[k], s.zb + halo, s.ze - halo));
                 CK(cudaEventRecord(ev[1], s.s_main));
-                // Planes at least `halo` away from a neighbour need nothing from it: their z pass and
-                // Hessian / eigen stage run while the exchange is still in flight; the planes next to
-                // a neighbour follow once the halo has arrived.
-                const int lo_n = s.index > 0 ? std::min(halo, nz) : 0;
-                const int hi_n = s.index < H->nslabs_total - 1 ? std::min(halo, nz - lo_n) : 0;
-                const int zi0 = s.zb + lo_n, zi1 = s.ze - hi_n;
-                if (zi1 > zi0) {
-                    Slab v = slab_view(H, s, zi0, zi1);
-                    RC(launch_z(H, v, sp));
-                    CK(cudaEventRecord(ev[2], s.s_main));
-                    RC(launch_voxel(H, v, sp, si));
-                } else {
-                    CK(cudaEventRecord(ev[2], s.s_main));
-                }
-                CK(cudaEventRecord(ev[3], s.s_main));
                 CK(cudaStreamWaitEvent(s.s_main, s.ev_halo, 0));
+                CK(cudaEventRecord(ev[2], s.s_main));
+                RC(launch_z(H, s, sp));
+                CK(cudaEventRecord(ev[3], s.s_main));
+            }
+            if (si + 1 < S) RC(xy_and_exchange(si + 1));
+            for (auto& s : H->slabs) {
+                CK(cudaSetDevice(s.dev));
+                cudaEvent_t* ev = s.ev_time + kEvPerScale * si;
                 CK(cudaEventRecord(ev[4], s.s_main));
-                if (lo_n > 0) {
-                    Slab v = slab_view(H, s, s.zb, zi0);
-                    RC(launch_z(H, v, sp));
-                    RC(launch_voxel(H, v, sp, si));
-                }
-                if (hi_n > 0) {
-                    Slab v = slab_view(H, s, zi1, s.ze);
-                    RC(launch_z(H, v, sp));
-                    RC(launch_voxel(H, v, sp, si));
-                }
+                RC(launch_voxel(H, s, sp, si));
                 CK(cudaEventRecord(ev[5], s.s_main));
             }
         } else if (H->overlap) {
@@ -878,11 +867,11 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
             cudaEvent_t* ev = s.ev_time + kEvPerScale * si;
             RC(launch_xy(H, s, sp, I_own[0], s.zb, s.ze));
             CK(cudaEventRecord(ev[1], s.s_main));
-            RC(launch_z(H, s, sp));
             CK(cudaEventRecord(ev[2], s.s_main));
-            RC(launch_voxel(H, s, sp, si));
+            RC(launch_z(H, s, sp));
             CK(cudaEventRecord(ev[3], s.s_main));
             CK(cudaEventRecord(ev[4], s.s_main));
+            RC(launch_voxel(H, s, sp, si));
             CK(cudaEventRecord(ev[5], s.s_main));
         }
     }
@@ -980,11 +969,11 @@ int collect(frangi_gpu* H, float* Jmin, float* Jmax)
         }
         for (int si = 0; si < S && !H->overlap; ++si) {
             const cudaEvent_t* e = ev + kEvPerScale * si;     // e[0] = end of the previous scale (or run start)
-            CK(cudaEventElapsedTime(&t, e[0], e[1])); H->last_ms[0] += t;   // xy smoothing
-            CK(cudaEventElapsedTime(&t, e[1], e[2])); H->last_ms[1] += t;   // z smoothing (interior part when multi-slab)
-            CK(cudaEventElapsedTime(&t, e[2], e[3])); H->last_ms[2] += t;   // Hessian / eigen (interior part)
-            CK(cudaEventElapsedTime(&t, e[3], e[4])); H->last_ms[4] += t;   // exposed halo wait
-            CK(cudaEventElapsedTime(&t, e[4], e[5])); H->last_ms[2] += t;   // boundary planes (z pass + Hessian / eigen)
+            CK(cudaEventElapsedTime(&t, e[0], e[1])); H->last_ms[0] += t;   // xy smoothing (multi-slab: of the first scale)
+            CK(cudaEventElapsedTime(&t, e[1], e[2])); H->last_ms[4] += t;   // exposed halo wait
+            CK(cudaEventElapsedTime(&t, e[2], e[3])); H->last_ms[1] += t;   // z smoothing
+            CK(cudaEventElapsedTime(&t, e[3], e[4])); H->last_ms[0] += t;   // multi-slab: xy smoothing of the NEXT scale, issued early
+            CK(cudaEventElapsedTime(&t, e[4], e[5])); H->last_ms[2] += t;   // Hessian / eigen
         }
         CK(cudaEventElapsedTime(&t, ev[kEvPerScale * S], ev[kEvPerScale * S + 1])); H->last_ms[3] += t;
         CK(cudaEventElapsedTime(&t, ev[0], ev[kEvPerScale * S + 1])); H->last_ms[5] += t;
