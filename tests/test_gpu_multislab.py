@@ -36,6 +36,25 @@ def test_slabs_on_one_device_equal_single_slab(nslabs, fma):
         assert np.array_equal(one[k], many[k]), k
 
 
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_six_scales_template_radius_above_true_radius(nslabs):
+    """sigma = 1, 3, 5 have z radii 2, 5, 8 but run in the radius-3, 6, 9 kernels: the z pass then reads planes with
+    zero taps, possibly halo planes still in flight; two runs on one handle, so stale halos of the last scale are
+    there when the first scale of the second run starts."""
+    I = make_volume(96, 64, 60, seed=35, n_neurites=6)
+    sigs = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0]
+    flags = FLAG_DIR_F32 | FLAG_SCALE_IDX
+    one = _run(I, sigs, (0,), flags)
+    l, h, w = I.shape
+    p = FrangiPlan(sigs, 2.0, .5, .5, 500., False, w, h, l, devices=(0,) * nslabs, flags=flags)
+    p.run(I, want_J8=True)
+    many = p.run(I, want_J8=True)
+    p.close()
+    assert many["Jmin"] == one["Jmin"] and many["Jmax"] == one["Jmax"]
+    for k in KEYS:
+        assert np.array_equal(one[k], many[k]), k
+
+
 def test_too_many_slabs_are_reduced_to_what_the_halo_allows():
     I = make_volume(40, 36, 24, seed=2, n_neurites=3)         # 24 planes, halo 11 -> at most 2 slabs
     one = _run(I, [6.0], (0,), 0)
