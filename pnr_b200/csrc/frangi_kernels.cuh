@@ -1032,6 +1032,82 @@ __device__ __forceinline__ void quad_hessians(const float* ring, const ZPlanes& 
 #undef DD
 }
 
+// Interior-plane second differences of the compacting kernel with the thread's z window kept in registers.  Of the
+// 26 loads of quad_hessians, the rows of planes z-1 and z-2 and the centre row of plane z were all loaded one plane
+// earlier (as planes z, z-1 and z+1): 10 loads and 40 shared-memory wavefronts per quad less (that kernel is bound
+// by the shared-memory pipe).  Same values, same operations: bit-identical.  `have` is false on the first plane of a
+// chunk and after a plane next to a z face.
+struct ZWin {
+    float b[8];      // row y of the next plane z   (this iteration's plane z+1 row y)
+    float mm[8];     // row y of the next plane z-1 (this iteration's plane z row y)
+    float mu[4], md[4];   // rows y-1, y+1 of the next plane z-1, columns x .. x+3
+    float pd[4];     // row y of the next plane z-2, columns x .. x+3
+};
+__device__ __forceinline__ void quad_hessians_reuse(const float* ring, const ZPlanes& zp, int o, bool have, ZWin& w, float2* Hxx,
+                                                    float2* Hxy, float2* Hxz, float2* Hyy, float2* Hyz, float2* Hzz)
+{
+    using T = HessTile;
+    const float* P0 = ring + zp.P0;
+    float a[8], b[8], c[8], t2[4], u2[4], pa[4], pd[4], mm[8], nn[8], mu[4], md[4], nu[4], nd[4];
+    *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(P0 + o - T::PW);
+    *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(P0 + o - T::PW + 4);
+    *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(P0 + o + T::PW);
+    *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(P0 + o + T::PW + 4);
+    *reinterpret_cast<float2*>(t2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 2);
+    *reinterpret_cast<float2*>(t2 + 2) = *reinterpret_cast<const float2*>(P0 + o - 2 * T::PW + 4);
+    *reinterpret_cast<float2*>(u2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 2);
+    *reinterpret_cast<float2*>(u2 + 2) = *reinterpret_cast<const float2*>(P0 + o + 2 * T::PW + 4);
+    *reinterpret_cast<float2*>(pa) = *reinterpret_cast<const float2*>(ring + zp.Pa + o + 2);
+    *reinterpret_cast<float2*>(pa + 2) = *reinterpret_cast<const float2*>(ring + zp.Pa + o + 4);
+    *reinterpret_cast<float4*>(nn) = *reinterpret_cast<const float4*>(ring + zp.Pzh + o);
+    *reinterpret_cast<float4*>(nn + 4) = *reinterpret_cast<const float4*>(ring + zp.Pzh + o + 4);
+    *reinterpret_cast<float2*>(nu) = *reinterpret_cast<const float2*>(ring + zp.Pzh + o - T::PW + 2);
+    *reinterpret_cast<float2*>(nu + 2) = *reinterpret_cast<const float2*>(ring + zp.Pzh + o - T::PW + 4);
+    *reinterpret_cast<float2*>(nd) = *reinterpret_cast<const float2*>(ring + zp.Pzh + o + T::PW + 2);
+    *reinterpret_cast<float2*>(nd + 2) = *reinterpret_cast<const float2*>(ring + zp.Pzh + o + T::PW + 4);
+    if (have) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { b[k] = w.b[k]; mm[k] = w.mm[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { mu[k] = w.mu[k]; md[k] = w.md[k]; pd[k] = w.pd[k]; }
+    } else {
+        *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(P0 + o);
+        *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(P0 + o + 4);
+        *reinterpret_cast<float2*>(pd) = *reinterpret_cast<const float2*>(ring + zp.Pd + o + 2);
+        *reinterpret_cast<float2*>(pd + 2) = *reinterpret_cast<const float2*>(ring + zp.Pd + o + 4);
+        *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(ring + zp.Pzl + o);
+        *reinterpret_cast<float4*>(mm + 4) = *reinterpret_cast<const float4*>(ring + zp.Pzl + o + 4);
+        *reinterpret_cast<float2*>(mu) = *reinterpret_cast<const float2*>(ring + zp.Pzl + o - T::PW + 2);
+        *reinterpret_cast<float2*>(mu + 2) = *reinterpret_cast<const float2*>(ring + zp.Pzl + o - T::PW + 4);
+        *reinterpret_cast<float2*>(md) = *reinterpret_cast<const float2*>(ring + zp.Pzl + o + T::PW + 2);
+        *reinterpret_cast<float2*>(md + 2) = *reinterpret_cast<const float2*>(ring + zp.Pzl + o + T::PW + 4);
+    }
+    const float qs = zp.qs;
+    const float2 qs2 = make_float2(qs, qs);
+#define PAIR(arr, i) make_float2((arr)[(i)], (arr)[(i) + 1])
+#define DD(hi, mid, lo) vmul(vsub(vsub(hi, mid), vsub(mid, lo)), qs2)
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int j = 2 * g;
+        const float2 f0 = PAIR(b, j + 2);
+        Hxx[g] = DD(PAIR(b, j + 4), f0, PAIR(b, j));
+        Hyy[g] = DD(PAIR(u2, j), f0, PAIR(t2, j));
+        Hzz[g] = DD(PAIR(pa, j), f0, PAIR(pd, j));
+        Hxy[g].x = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 3], c[j + 1]), __fsub_rn(a[j + 3], a[j + 1])), qs);
+        Hxy[g].y = __fmul_rn(__fsub_rn(__fsub_rn(c[j + 4], c[j + 2]), __fsub_rn(a[j + 4], a[j + 2])), qs);
+        Hxz[g].x = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 3], nn[j + 1]), __fsub_rn(mm[j + 3], mm[j + 1])), qs);
+        Hxz[g].y = __fmul_rn(__fsub_rn(__fsub_rn(nn[j + 4], nn[j + 2]), __fsub_rn(mm[j + 4], mm[j + 2])), qs);
+        Hyz[g] = vmul(vsub(vsub(PAIR(nd, j), PAIR(nu, j)), vsub(PAIR(md, j), PAIR(mu, j))), qs2);
+    }
+#undef PAIR
+#undef DD
+    // the window of the next plane
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { w.mm[k] = b[k]; w.b[k] = nn[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { w.pd[k] = mm[k + 2]; w.mu[k] = a[k + 2]; w.md[k] = c[k + 2]; }
+}
+
 template <int MODE, bool BRIGHT = false>
 __global__ void __launch_bounds__(HessTile::NT, HESS_MIN_CTAS)
 hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
@@ -1291,6 +1367,8 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     const uint32_t q_s = smem_u32(qf);
     const int o_quad = (yl + 2) * T::PW + 4 * tx;
     int pos0 = (yl << 7) | (4 * tx);              // + (z - zs) << 10
+    ZWin zwin;
+    bool win_ok = false;
 
     // Phase B on entries [first, first + count) (ring positions, first even): PAIRS independent packed pairs per thread
     auto drain = [&](unsigned first, int count) {
@@ -1342,8 +1420,8 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         jp += plane_vox;
         if (row_ok && z + 1 < ze) load_j(jp);
         if (row_ok) {
-            if (z_general) quad_hessians<true>(ring, z_planes(tr.o, z, l, p.k.sigma2), o_quad, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
-            else quad_hessians<false>(ring, z_planes_interior(tr.o, p.k.sigma2), o_quad, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+            if (z_general) { quad_hessians<true>(ring, z_planes(tr.o, z, l, p.k.sigma2), o_quad, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz); win_ok = false; }
+            else { quad_hessians_reuse(ring, z_planes_interior(tr.o, p.k.sigma2), o_quad, win_ok, zwin, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz); win_ok = true; }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 const float2 sxy = vadd(Hxx[g], Hyy[g]), sxz = vadd(Hxx[g], Hzz[g]), syz = vadd(Hyy[g], Hzz[g]);
