@@ -189,6 +189,9 @@ int frangi_gpu_frangi2d(const uint8_t* I_host, int w, int h, const float* sigmas
                         unsigned flags);
 int frangi_gpu_hessian2d(const uint8_t* I_host, int w, int h, float sigma, float* Dyy, float* Dxy,
                          float* Dxx, int device, unsigned flags);
+/* Frangi::imgaussian(I,w,h,sig,F), the 2-D overload (frangi.h:44, frangi.cpp:563-645): F_host = w*h
+ * floats, always the separately rounded smoothing (bit-identical to the reference). */
+int frangi_gpu_imgaussian2d(const uint8_t* I_host, int w, int h, float sigma, float* F_host, int device);
 
 /* ---- f4, second part: the helpers of the plugin's soma branch -----------------------
  * (Advantra_plugin.cpp:2426-2440, only reached with somaradius > 0).  Host buffers of
@@ -198,6 +201,10 @@ int frangi_gpu_hessian2d(const uint8_t* I_host, int w, int h, float sigma, float
   *   Frangi::imgaussian(I,w,h,l,sig)  frangi.h:43, frangi.cpp:786-877   xy Gaussian in place; the y
  *                                    pass accumulates into the unsigned char, truncating per tap */
 int frangi_gpu_imerode(const uint8_t* I_host, int w, int h, int l, float rad, uint8_t* E_host, int device);
+/*   Frangi::imerode(I,w,h,l,rad,zdist,E)  frangi.h:46, frangi.cpp:971-1108  the same followed by the minimum
+ *                                    along z over ceil(rad/zdist) planes each side (skipped when l == 1) */
+int frangi_gpu_imerode_z(const uint8_t* I_host, int w, int h, int l, float rad, float zdist, uint8_t* E_host,
+                         int device);
 int frangi_gpu_imdilate(uint8_t* I_host, int w, int h, int l, float rad, int device);
 int frangi_gpu_imgaussian_xy(uint8_t* I_host, int w, int h, int l, float sig, int device);
 

@@ -204,6 +204,18 @@ class Oracle:
         self.lib.oracle_morph_xy(_p(I, _u8p), w, h, l, rad, 0, _p(out, _u8p))
         return out
 
+    def imerode_z(self, I, rad, zdist):
+        """Frangi::imerode(I,w,h,l,rad,zdist,E) (frangi.h:46)."""
+        I, w, h, l = _check_vol(I)
+        out = np.empty_like(I)
+        self.lib.oracle_imerode_z.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _u8p]
+        self.lib.oracle_imerode_z(_p(I, _u8p), w, h, l, rad, zdist, _p(out, _u8p))
+        return out
+
+    def imgaussian2d(self, I, sigma):
+        """Frangi::imgaussian(I,w,h,sig,F) (frangi.h:44): the smoothed image hessian2d starts from."""
+        return self.hessian2d(I, sigma)["F"]
+
     def imgaussian_xy(self, I, sigma):
         I, w, h, l = _check_vol(I)
         out = I.copy()
@@ -349,6 +361,54 @@ class Reference:
         out = I.copy()
         self.lib.ref_imgaussian_xy(_p(out, _u8p), w, h, l, sigma)
         return out
+
+    # ---- the members no live code calls (frangi.h:28-31,44,46,51); present when oracle/_ref was built from this tree
+    @property
+    def has_cold(self):
+        return hasattr(self.lib, "ref_imerode_z")
+
+    def imerode_z(self, I, rad, zdist):
+        I, w, h, l = _check_vol(I)
+        out = np.empty_like(I)
+        f = self.lib.ref_imerode_z
+        f.restype = None
+        f.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _u8p]
+        f(_p(I, _u8p), w, h, l, rad, zdist, _p(out, _u8p))
+        return out
+
+    def imgaussian2d(self, I, sigma):
+        I = np.ascontiguousarray(I, np.uint8)
+        h, w = I.shape
+        F = np.empty(I.shape, np.float32)
+        f = self.lib.ref_imgaussian2d
+        f.restype = None
+        f.argtypes = [_u8p, C.c_int, C.c_int, C.c_float, _f32p]
+        f(_p(I, _u8p), w, h, sigma, _p(F, _f32p))
+        return F
+
+    def unit_directions(self, three_d, ndir):
+        out = np.empty((ndir, 3), np.float32)
+        f = self.lib.ref_unit_directions
+        f.restype = None
+        f.argtypes = [C.c_int, C.c_int, _f32p]
+        f(int(three_d), ndir, _p(out, _f32p))
+        return out
+
+    def direction_idx(self, v, table):
+        table = np.ascontiguousarray(table, np.float32)
+        f = self.lib.ref_direction_idx
+        f.restype = C.c_int
+        f.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, _f32p, C.c_int]
+        three_d = len(v) == 3
+        return f(int(three_d), v[0], v[1], v[2] if three_d else 0.0, _p(table, _f32p), len(table))
+
+    def interpz(self, x, y, z, img):
+        img = np.ascontiguousarray(img, np.float32)
+        l, h, w = img.shape
+        f = self.lib.ref_interpz
+        f.restype = C.c_float
+        f.argtypes = [C.c_int, C.c_int, C.c_float, _f32p, C.c_int, C.c_int, C.c_int]
+        return f(x, y, z, _p(img, _f32p), w, h, l)
 
     def trace(self, I, J8, Vx, Vy, Vz, sigmas, tolerance=5.0, znccth=0.3, kappa=3.0, step=2, ni=200, np_=20,
               zdist=2.0, nodepervol=4, max_traces=5000):

@@ -684,6 +684,34 @@ ORACLE_API int oracle_morph_xy(const uint8_t *I, int w, int h, int l, float rad,
     return 0;
 }
 
+/* Frangi::imerode(I,w,h,l,rad,zdist,E) (frangi.cpp:971-1108): the xy erosion above followed by the minimum along z
+ * over [z - ceil(rad/zdist), z + ceil(rad/zdist)] clamped; a single plane skips the z pass (:1062-1064). */
+ORACLE_API int oracle_imerode_z(const uint8_t *I, int w, int h, int l, float rad, float zdist, uint8_t *out)
+{
+    const size_t n = (size_t)w * h * l;
+    uint8_t *K = (uint8_t *)malloc(n);
+    if (!K) return -1;
+    if (oracle_morph_xy(I, w, h, l, rad, 1, K)) { free(K); return -1; }
+    if (l == 1) {
+        memcpy(out, K, n);
+    } else {
+        const int Lz = (int)ceilf(rad / zdist);
+        const size_t plane = (size_t)w * h;
+        for (int z = 0; z < l; ++z)
+            for (size_t q = 0; q < plane; ++q) {
+                uint8_t v = K[(size_t)z * plane + q];
+                for (int k = -Lz; k <= Lz; ++k) {
+                    int zs = z + k < 0 ? 0 : (z + k > l - 1 ? l - 1 : z + k);
+                    uint8_t c = K[(size_t)zs * plane + q];
+                    if (c < v) v = c;
+                }
+                out[(size_t)z * plane + q] = v;
+            }
+    }
+    free(K);
+    return 0;
+}
+
 /* Frangi::imgaussian(I,w,h,l,sig) (frangi.cpp:786-877): xy Gaussian of a uint8 volume in place.  The x pass
  * accumulates in float32 (:806-838); the y pass accumulates INTO the unsigned char -- `I[i0] = 0; I[i0] += K*G` --
  * so every tap is (unsigned char)((float)I[i0] + K*G) (:841-873). */

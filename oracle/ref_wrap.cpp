@@ -125,6 +125,45 @@ void ref_imdilate(unsigned char* I, int w, int h, int l, float rad) { QuietCout 
 __attribute__((visibility("default")))
 void ref_imgaussian_xy(unsigned char* I, int w, int h, int l, float sig) { QuietCout q; Frangi::imgaussian(I, w, h, l, sig); }
 
+// the overloads no live code calls: z-scaled erosion (frangi.h:46), 2-D smoothing (frangi.h:44)
+__attribute__((visibility("default")))
+void ref_imerode_z(unsigned char* I, int w, int h, int l, float rad, float zdist, unsigned char* E) { QuietCout q; Frangi::imerode(I, w, h, l, rad, zdist, E); }
+__attribute__((visibility("default")))
+void ref_imgaussian2d(unsigned char* I, int w, int h, float sig, float* F) { QuietCout q; Frangi::imgaussian(I, w, h, sig, F); }
+
+// host helpers of the class (frangi.h:28-31,51): direction tables, nearest table entry, z interpolation
+__attribute__((visibility("default")))
+void ref_unit_directions(int three_d, int ndir, float* out /* ndir x 3 */)
+{
+    QuietCout q;
+    std::vector<float> s(1, 2.0f);
+    Frangi f(s, 1.0f, .5f, .5f, 500.f, .5f, 15.f);
+    std::vector<std::vector<float> > t;
+    if (three_d) f.generate_3d_unit_directions((unsigned char)ndir, t);
+    else f.generate_2d_unit_directions((unsigned char)ndir, t);
+    for (size_t k = 0; k < t.size(); ++k)
+        for (int c = 0; c < 3; ++c) out[3 * k + c] = t[k][c];
+}
+__attribute__((visibility("default")))
+int ref_direction_idx(int three_d, float vx, float vy, float vz, const float* table, int ndir)
+{
+    QuietCout q;
+    std::vector<float> s(1, 2.0f);
+    Frangi f(s, 1.0f, .5f, .5f, 500.f, .5f, 15.f);
+    std::vector<std::vector<float> > t(ndir, std::vector<float>(3));
+    for (int k = 0; k < ndir; ++k)
+        for (int c = 0; c < 3; ++c) t[k][c] = table[3 * k + c];
+    return three_d ? f.get_direction_idx(vx, vy, vz, t) : f.get_direction_idx(vx, vy, t);
+}
+__attribute__((visibility("default")))
+float ref_interpz(int x, int y, float z, float* img, int w, int h, int l)
+{
+    QuietCout q;
+    std::vector<float> s(1, 2.0f);
+    Frangi f(s, 1.0f, .5f, .5f, 500.f, .5f, 15.f);
+    return f.interpz(x, y, z, img, w, h, l);
+}
+
 // Seeds are returned as rows of 6 floats (x, y, z, vx, vy, vz).  Returns the
 // number of seeds found; at most `cap` rows are written.
 __attribute__((visibility("default")))

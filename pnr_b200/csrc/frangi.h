@@ -8,10 +8,12 @@
 // Same public field names, constructor and member signatures as the reference for
 // everything ON the path (frangi.h:8-24,33,35,42); every call forwards to the C-ABI
 // of include/frangi_gpu.h.  The 2-D pair frangi2d / hessian2d (frangi.h:38,40) is
-// provided too, and so are the soma helpers imerode / imdilate / in-place xy imgaussian
-// (frangi.h:47,49,43).  Not provided: the z-scaled imerode overload (frangi.h:46, never
-// called), the direction tables and the public eigen-solver entry points (dead code in the
-// plugin).
+// provided too, and so are the soma helpers imerode (both overloads) / imdilate / in-place xy
+// imgaussian (frangi.h:46,47,49,43) and the 2-D imgaussian (frangi.h:44).  The members that are
+// plain host helpers in the reference -- the public eigen-solver entry points (frangi.h:53-58;
+// Advantra_plugin.cpp:1727 calls eigen_decomposition_static), the direction tables
+// (frangi.h:18-20,28-31) and interpz (frangi.h:51) -- are host code here too
+// (frangi_shim_host.cpp), so every Frangi:: symbol of the reference header links.
 //
 // Error behaviour: the reference's members return void and fail only by uncaught
 // std::bad_alloc; here a failed GPU call throws std::runtime_error carrying
@@ -33,6 +35,10 @@ public:
     float BetaOne;   // 2-D only (frangi2d)
     float BetaTwo;   // 2-D only
     float C;
+    // direction tables (frangi.h:18-20): declared by the reference, filled by nobody on the live path
+    std::vector<std::vector<float> > Vxyz;
+    static unsigned char ndirs2d;
+    static unsigned char ndirs3d;
     bool blackwhite; // true: dark ridges, false: bright ridges (default, frangi.cpp:54)
 
     // ---- additions (defaults keep the reference's behaviour) ----
@@ -43,6 +49,12 @@ public:
     ~Frangi();
     Frangi(const Frangi&) = delete;
     Frangi& operator=(const Frangi&) = delete;
+
+    // frangi.h:28-31 (host helpers, frangi_shim_host.cpp)
+    void generate_3d_unit_directions(unsigned char Ndir, std::vector<std::vector<float> >& Vxyz);
+    void generate_2d_unit_directions(unsigned char Ndir, std::vector<std::vector<float> >& Vxyz);
+    unsigned char get_direction_idx(float vx, float vy, float vz, std::vector<std::vector<float> > Vxyz);
+    unsigned char get_direction_idx(float vx, float vy, std::vector<std::vector<float> > Vxyz);
 
     // frangi.h:33 -- caller owns every buffer (w*h*l elements each), callee only fills
     void frangi3d(unsigned char* I, int w, int h, int l, float* J, float& Jmin, float& Jmax,
@@ -72,6 +84,19 @@ public:
     static void imgaussian(unsigned char* I, int w, int h, int l, float sig_);
     static void imerode(unsigned char* I, int w, int h, int l, float rad, unsigned char* E);
     static void imdilate(unsigned char* I, int w, int h, int l, float rad);
+    // frangi.h:44,46 -- the overloads no live code calls (2-D smoothing, z-scaled erosion); on the device as well
+    static void imgaussian(unsigned char* I, int w, int h, float sig_, float* F);
+    static void imerode(unsigned char* I, int w, int h, int l, float rad, float zdist_, unsigned char* E);
+
+    // frangi.h:51-58 (host helpers, frangi_shim_host.cpp); eigen_decomposition_static is what
+    // Advantra_plugin.cpp:1727 calls
+    float interpz(int x, int y, float z, float* img, int w, int h, int l);
+    void eigen_decomposition(double A[3][3], double V[3][3], double d[3]);
+    static void eigen_decomposition_static(double A[3][3], double V[3][3], double d[3]);
+    static void tred2(double V[3][3], double d[3], double e[3]);
+    static void tql2(double V[3][3], double d[3], double e[3]);
+    static double hypot2(double x, double y);
+    static double absd(double val) { return val > 0 ? val : -val; }
 
 private:
     frangi_gpu* handle_;

@@ -660,6 +660,7 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
     if (p.zchunk >= (1 << 21)) return launch_voxel_t<1, true>(p, nblocks, nshell, s.s_main);   // packed z offset has 21 bits
     // later scale of a bright-ridge run: the compacting kernel (its own 128 x 8 tiling), then the shell
     if (nblocks > 0) {
+        p.ntx = (H->w - 2 - HessTileC::X_FIRST + HessTileC::TX - 1) / HessTileC::TX;   // tiles cover x up to w-3
         p.nty = (H->h + HessTileC::TY - 1) / HessTileC::TY;
         nblocks = (long long)p.ntx * p.nty * nzc;
         if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
@@ -1668,6 +1669,29 @@ FRANGI_API int frangi_gpu_hessian2d(const uint8_t* I_host, int w, int h, float s
     return run_2d(I_host, w, h, &sigma, 1, .5f, 15.f, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, D, device, flags);
 }
 
+// Frangi::imgaussian(I, w, h, sig, F), the 2-D overload (frangi.h:44, frangi.cpp:563-645): K1 on one plane in the
+// separately rounded mode (same taps, clamp and accumulation order as the 3-D x and y passes)
+FRANGI_API int frangi_gpu_imgaussian2d(const uint8_t* I_host, int w, int h, float sigma, float* F_host, int device)
+{
+    if (!I_host || !F_host) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    if (w < 1 || h < 1 || (long long)w * h > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "bad image %d x %d", w, h);
+    if (!(sigma > 0)) return fail(FRANGI_GPU_EINVAL, "sigma must be > 0");
+    RC(check_device(device));
+    CK(cudaSetDevice(device));
+    const int fpitch = (w + 31) / 32 * 32;
+    Dev2D d;
+    CK(cudaMalloc(&d.I, (size_t)w * h));
+    CK(cudaMalloc(&d.F, sizeof(float) * (size_t)fpitch * h));
+    CK(cudaMemcpy(d.I, I_host, (size_t)w * h, cudaMemcpyHostToDevice));
+    ScalePlan sp;
+    sp.sigma = sigma; sp.sigma2 = sigma * sigma;
+    RC(plan_taps(sp.sigma, sp.rxy, sp.rxy_t, sp.txy));
+    RC(launch_xy_planes(d.I, d.F, w, h, 1, fpitch, (long long)fpitch * h, sp, 0u, 0));
+    CK(cudaMemcpy2D(F_host, sizeof(float) * (size_t)w, d.F, sizeof(float) * (size_t)fpitch, sizeof(float) * (size_t)w, h,
+                    cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // ---- f4, second part: the soma helpers (soma_kernels.cuh) -------------------------------------------------
 namespace {
 struct DevSoma {
@@ -1710,6 +1734,33 @@ int morph(const uint8_t* I_host, int w, int h, int l, float rad, uint8_t* out_ho
 FRANGI_API int frangi_gpu_imerode(const uint8_t* I_host, int w, int h, int l, float rad, uint8_t* E_host, int device)
 {
     return morph<true>(I_host, w, h, l, rad, E_host, device);
+}
+
+// the z-scaled overload (frangi.h:46, frangi.cpp:971-1108): x, y as above, then the minimum along z over
+// ceil(rad / zdist) planes each side; a single plane skips the z pass (:1062-1064)
+FRANGI_API int frangi_gpu_imerode_z(const uint8_t* I_host, int w, int h, int l, float rad, float zdist, uint8_t* E_host, int device)
+{
+    RC(soma_args(I_host, w, h, l, device));
+    if (!E_host || !(rad >= 0) || !(zdist > 0)) return fail(FRANGI_GPU_EINVAL, "bad argument");
+    const int L = (int)std::ceil(rad), Lz = (int)std::ceil(rad / zdist);
+    const size_t n = (size_t)w * h * l;
+    DevSoma d;
+    CK(cudaMalloc(&d.a, n));
+    CK(cudaMalloc(&d.b, n));
+    CK(cudaMemcpy(d.a, I_host, n, cudaMemcpyHostToDevice));
+    const dim3 grid((w + 255) / 256, h, (unsigned)std::min(l, 4096));
+    morph_pass_kernel<true, false><<<grid, 256>>>(d.a, d.b, w, h, l, L);
+    morph_pass_kernel<true, true><<<grid, 256>>>(d.b, d.a, w, h, l, L);
+    g_launches += 2;
+    const uint8_t* res = d.a;
+    if (l > 1) {
+        morph_min_z_kernel<<<grid, 256>>>(d.a, d.b, w, h, l, Lz);
+        g_launches++;
+        res = d.b;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(E_host, res, n, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 FRANGI_API int frangi_gpu_imdilate(uint8_t* I_host, int w, int h, int l, float rad, int device)

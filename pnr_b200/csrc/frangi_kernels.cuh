@@ -1263,14 +1263,366 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
 // thread takes two entries through the packed eigen stage and updates J / V where the response
 // beats the stored one, so the expensive stage always runs with full lanes.  The queue persists
 // across planes and is flushed at the end of the chunk.
+#ifndef K3C_SLOTS
+#define K3C_SLOTS 6
+#endif
+#ifndef K3C_DRAIN_UNROLL
+#define K3C_DRAIN_UNROLL 1
+#endif
+#ifndef K3C_V1
+// ---- K3a' (current form) ------------------------------------------------------------------------------------
+// The first form (below, -DK3C_V1) read every quad's 26 row segments of the five planes from shared memory per
+// plane: 133 shared-memory wavefronts per warp and plane, which is what bounded it (the shared-memory pipe was 87 %
+// busy during phase A; profiles/r1n).  Testing the diagonal first and fetching the rest only for quads with a
+// survivor does not help: the survivors are noise voxels, spread evenly (57 % of the quads hold one).  This form cuts
+// the traffic itself:
+//  * tiles are 16-byte aligned with the quads (the box starts 4 columns left of the tile), so a row segment of a
+//    quad is ONE 128-bit load with a lane stride of 16 bytes -- 4 wavefronts for 512 useful bytes, where the
+//    2-column offset of the first form needed two 64-bit loads (8 wavefronts);
+//  * the columns next to a quad (x-2, x-1, x+4, x+5) come from the neighbour lanes' registers by warp shuffle
+//    (lanes 0 and 31 take them from the tile's halo columns);
+//  * a thread keeps its own row of the planes z-2 .. z+2 and the x first differences of the planes z-1 .. z+1 in
+//    register rings (the z window marches with the thread), rotated by renaming: the plane loop dispatches on
+//    (z mod 5) to five instantiations of phase A whose register indices are static.
+// Per quad and plane: 9 aligned 128-bit loads (own row of plane z+2; rows y-1, y+1 of planes z-1, z, z+1; rows
+// y-2, y+2 of plane z), 8 shuffles and 3 single-lane halo loads = 48 wavefronts instead of 133.
+// The stored response J of a survivor is fetched at the drain (a gather over the ~20 % of the voxels that reach
+// it) instead of being streamed for every voxel.  Same operations on the same operands in the same order as
+// quad_hessians<false>: bit-identical second differences.
+struct HessTileC {                               // 128 x 8 voxels, one row per warp, one quad per thread
+    static constexpr int TX = 128, TY = 8, NT = 256;
+    static constexpr int XH = 4;                 // box columns left / right of the tile (16-byte aligned quads)
+    static constexpr int PW = TX + 2 * XH;       // 136 floats per tile row
+    static constexpr int PH = TY + 4;
+    static constexpr int PLANE = PW * PH;        // 1632 floats: the TMA box
+    static constexpr int SLOT = (PLANE * 4 + 127) / 128 * 32;   // 1632 floats (6528 bytes)
+    static constexpr int SLOTS = K3C_SLOTS;      // planes z-2 .. z+2 in use + SLOTS - 5 planes in flight
+    static constexpr int RING_BYTES = SLOTS * SLOT * 4;
+    static constexpr int X_FIRST = 0;            // tile bx covers the voxels x = TX * bx + [0, TX); x = 0, 1 are masked (shell)
+};
+struct HessQueue {
+    static constexpr int PAIRS = 2;                                  // packed pairs per thread per drain
+    static constexpr int BATCH = 2 * PAIRS * HessTileC::NT;          // 1024 entries per drain
+    static constexpr int APPEND = HessTileC::TX * HessTileC::TY;     // most one plane can add (1024)
+    // Appends only happen right after the plane barrier, when at most BATCH - 1 entries are pending and no drain is
+    // in flight, so BATCH + APPEND ring entries can never collide; a power of two so that the ring index is a mask.
+    static constexpr int CAP = 2048;
+    static_assert(CAP >= BATCH + APPEND, "queue too small");
+    // structure of arrays: field f of entry e at float f * CAP + e; fields = Dxx, Dxy, Dxz, Dyy, Dyz, Dzz, packed position.
+    // A drain reads entries (e, e + 1), e even, as one 64-bit load per field: the packed register pair of the eigen stage.
+    static constexpr int FIELDS = 7;
+    static constexpr int DRAIN_UNROLL = K3C_DRAIN_UNROLL;            // 1: the pairs of a drain go through the eigen stage one after the other (registers)
+    static constexpr int BYTES = CAP * FIELDS * 4;
+    static constexpr int SMEM_BYTES = HessTileC::RING_BYTES + BYTES + HessTileC::SLOTS * 8 + 16;   // + mbarriers + tail counter
+};
+
+template <int N> struct IntC { static constexpr int value = N; };
+
+// the five resident planes of a z-marching tile as a field for hessian_at_face (planes next to a z face)
+struct RingField {
+    const float* ring;
+    int o0, o1, o2, o3, o4;     // ring offsets of planes zc-2 .. zc+2
+    int zc, xb, yb;             // centre plane; global coordinates of tile entry (0, 0)
+    int w, h, l;
+    __device__ __forceinline__ float at(int x, int y, int z) const
+    {
+        const int k = z - zc;
+        const int o = k <= -2 ? o0 : (k == -1 ? o1 : (k == 0 ? o2 : (k == 1 ? o3 : o4)));
+        return ring[o + (y - yb) * HessTileC::PW + (x - xb)];
+    }
+};
+
+__global__ void __launch_bounds__(HessTileC::NT, 2)
+hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
+{
+    using T = HessTileC;
+    using Q = HessQueue;
+    extern __shared__ __align__(128) float ring[];
+    float* qf = ring + T::SLOTS * T::SLOT;                                 // FIELDS arrays of CAP floats
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(qf + Q::FIELDS * Q::CAP);
+    unsigned* s_tail = reinterpret_cast<unsigned*>(mbar + T::SLOTS);       // entries ever appended (ring index = tail % CAP)
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    int bid = blockIdx.x;
+    const int bx = bid % p.ntx; bid /= p.ntx;
+    const int by = bid % p.nty;
+    const int bz = bid / p.nty;
+    const int x0 = bx * T::TX - T::XH, y0 = by * T::TY - 2;   // global coordinates of tile entry (0, 0); x0 is a multiple of 4 floats (TMA)
+    const int w = p.f.w, h = p.f.h, l = p.f.l;
+    const int zs = p.z_begin + bz * p.zchunk;
+    const int ze = min(zs + p.zchunk, p.z_begin + p.nz);
+    if (zs >= ze) return;
+    if (tid == 0) *s_tail = 0;
+
+    TileRing<T> tr;
+    tr.init(ring, mbar, tid);
+    __syncthreads();
+    constexpr int PF = T::SLOTS - 5;              // planes in flight beyond z+2
+    if (tid == 0)
+        for (int q = zs - 2; q <= min(zs + 1 + PF, ze + 1); ++q) tr.issue(&p.tmap, x0, y0, q, p.f.base, l);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) tr.wait_next();
+
+    const int xq = bx * T::TX + 4 * tx;           // first voxel of the quad
+    const int yl = ty;                            // one tile row per warp
+    const int yrow = by * T::TY + yl;
+    const bool row_ok = yrow >= 2 && yrow <= h - 3;
+    bool m[4];                                    // voxel j of the quad is an interior voxel
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = row_ok && xq + j >= 2 && xq + j <= w - 3;
+    float vmax = 0.0f;
+    unsigned head = 0;        // entries [head, tail) are pending; every thread carries the same value
+    const int o_own = (yl + 2) * T::PW + T::XH + 4 * tx;      // tile entry of (xq, yrow)
+    const int o_row = (yl + 2) * T::PW;                       // tile entry 0 of the warp's row
+    int pos0 = (yl << 7) | (4 * tx);              // + (z - zs) << 10
+    const float qs = 0.25f * p.k.sigma2;
+    const float2 qs2 = make_float2(qs, qs);
+    const unsigned below = (1u << tx) - 1u;
+    const bool edge_lane = tx == 0 || tx == 31;
+
+    // Register rings (slot (rot + k) % 5 holds plane z-2+k): C = the quad's own row, G = its x first differences
+    // F[x+1] - F[x-1] (planes z-1 .. z+1 live).  E0 = the columns x-2, x-1, x+4, x+5 of plane z.
+    float C[5][4], G[5][4], E0[4];
+    bool have = false;        // the rings hold planes z-2 .. z+1 (and G z-1, z; E0) of the plane about to be processed
+
+    // columns x-2, x-1, x+4, x+5 of a row whose quad is c[0..3]: the neighbour lanes' registers, the tile's halo
+    // columns for lanes 0 and 31 (`rowp` = tile entry 0 of the row)
+    auto edges4 = [&](const float* c, const float* rowp, float* e) {
+        e[0] = __shfl_up_sync(0xffffffffu, c[2], 1); e[1] = __shfl_up_sync(0xffffffffu, c[3], 1);
+        e[2] = __shfl_down_sync(0xffffffffu, c[0], 1); e[3] = __shfl_down_sync(0xffffffffu, c[1], 1);
+        if (edge_lane) {
+            const float2 v = *reinterpret_cast<const float2*>(rowp + (tx ? T::XH + T::TX : T::XH - 2));
+            if (tx) { e[2] = v.x; e[3] = v.y; } else { e[0] = v.x; e[1] = v.y; }
+        }
+    };
+    // columns x-1, x+4 only
+    auto edges2 = [&](const float* c, const float* rowp, float& lo, float& hi) {
+        lo = __shfl_up_sync(0xffffffffu, c[3], 1);
+        hi = __shfl_down_sync(0xffffffffu, c[0], 1);
+        if (edge_lane) {
+            const float v = rowp[tx ? T::XH + T::TX : T::XH - 1];
+            if (tx) hi = v; else lo = v;
+        }
+    };
+    // x first differences of the quad: F[x+j+1] - F[x+j-1]
+    auto xdiff = [&](const float* c, float lo, float hi, float* g) {
+        g[0] = __fsub_rn(c[1], lo); g[1] = __fsub_rn(c[2], c[0]); g[2] = __fsub_rn(c[3], c[1]); g[3] = __fsub_rn(hi, c[2]);
+    };
+    auto ld4a = [&](float* d, const float* s) { *reinterpret_cast<float4*>(d) = *reinterpret_cast<const float4*>(s); };
+
+    // survivors of the quad go to the queue
+    auto append = [&](const bool* surv, const float2* Hxx, const float2* Hxy, const float2* Hxz, const float2* Hyy,
+                      const float2* Hyz, const float2* Hzz, const unsigned* slot) {
+        typedef Lanes<float2> L2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (surv[j]) {
+                float* e = qf + (slot[j] & (Q::CAP - 1));
+                e[0] = L2::get(Hxx[j >> 1], j & 1); e[Q::CAP] = L2::get(Hxy[j >> 1], j & 1);
+                e[2 * Q::CAP] = L2::get(Hxz[j >> 1], j & 1); e[3 * Q::CAP] = L2::get(Hyy[j >> 1], j & 1);
+                e[4 * Q::CAP] = L2::get(Hyz[j >> 1], j & 1); e[5 * Q::CAP] = L2::get(Hzz[j >> 1], j & 1);
+                e[6 * Q::CAP] = __int_as_float(pos0 + j);
+            }
+    };
+    // queue slots of the quad's survivors: warp-aggregated, one shared atomic per warp and plane (convergent code)
+    auto slots = [&](const bool* surv, unsigned* slot) {
+        const unsigned b0 = __ballot_sync(0xffffffffu, surv[0]), b1 = __ballot_sync(0xffffffffu, surv[1]);
+        const unsigned b2 = __ballot_sync(0xffffffffu, surv[2]), b3 = __ballot_sync(0xffffffffu, surv[3]);
+        if ((b0 | b1 | b2 | b3) == 0u) return;
+        const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+        unsigned base = 0;
+        if (tx == 0) base = atomicAdd(s_tail, (unsigned)(n0 + n1 + n2 + n3));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        slot[0] = base + __popc(b0 & below); slot[1] = base + n0 + __popc(b1 & below);
+        slot[2] = base + n0 + n1 + __popc(b2 & below); slot[3] = base + n0 + n1 + n2 + __popc(b3 & below);
+    };
+    // the diagonal-sum test (Ky Fan): a voxel whose response can be positive has Dxx+Dyy, Dxx+Dzz, Dyy+Dzz <= 0
+    auto test = [&](const float2* Hxx, const float2* Hyy, const float2* Hzz, bool* surv) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const float2 sxy = vadd(Hxx[g], Hyy[g]), sxz = vadd(Hxx[g], Hzz[g]), syz = vadd(Hyy[g], Hzz[g]);
+            surv[2 * g] = m[2 * g] && fmaxf(fmaxf(sxy.x, sxz.x), syz.x) <= 0.0f;
+            surv[2 * g + 1] = m[2 * g + 1] && fmaxf(fmaxf(sxy.y, sxz.y), syz.y) <= 0.0f;
+        }
+    };
+#define PAIR(arr, i) make_float2((arr)[(i)], (arr)[(i) + 1])
+#define DD(hi, mid, lo) vmul(vsub(vsub(hi, mid), vsub(mid, lo)), qs2)
+    // phase A of an interior plane (2 <= z <= l-3) with the register rings at rotation R
+    auto phase_a = [&](auto rc) {
+        constexpr int R = decltype(rc)::value;
+        float (&Cm2)[4] = C[R % 5];
+        float (&Cm1)[4] = C[(R + 1) % 5];
+        float (&C0)[4] = C[(R + 2) % 5];
+        float (&Cp1)[4] = C[(R + 3) % 5];
+        float (&Cp2)[4] = C[(R + 4) % 5];
+        float (&Gm1)[4] = G[(R + 1) % 5];
+        float (&G0)[4] = G[(R + 2) % 5];
+        float (&Gp1)[4] = G[(R + 3) % 5];
+        const float* Pm1 = ring + tr.o[1];
+        const float* P0 = ring + tr.o[2];
+        const float* Pp1 = ring + tr.o[3];
+        if (!have) {          // first plane of the chunk, or the plane after one next to a z face (warp-uniform)
+            ld4a(Cm2, ring + tr.o[0] + o_own); ld4a(Cm1, Pm1 + o_own); ld4a(C0, P0 + o_own); ld4a(Cp1, Pp1 + o_own);
+            float lo, hi;
+            edges2(Cm1, Pm1 + o_row, lo, hi);
+            xdiff(Cm1, lo, hi, Gm1);
+            edges4(C0, P0 + o_row, E0);
+            xdiff(C0, E0[1], E0[2], G0);
+        }
+        // every thread loads (rows beyond the volume are zero-filled tile rows): shuffles need all lanes, and ring rows
+        // written unconditionally are what lets the compiler see that a rotated-out row is dead
+        ld4a(Cp2, ring + tr.o[4] + o_own);
+        float E1[4];
+        edges4(Cp1, Pp1 + o_row, E1);
+        xdiff(Cp1, E1[1], E1[2], Gp1);
+        float a[4], c[4], mu[4], md[4], nu[4], nd[4], t2[4], u2[4];
+        ld4a(a, P0 + o_own - T::PW); ld4a(c, P0 + o_own + T::PW);
+        ld4a(t2, P0 + o_own - 2 * T::PW); ld4a(u2, P0 + o_own + 2 * T::PW);
+        ld4a(mu, Pm1 + o_own - T::PW); ld4a(md, Pm1 + o_own + T::PW);
+        ld4a(nu, Pp1 + o_own - T::PW); ld4a(nd, Pp1 + o_own + T::PW);
+        float alo, ahi, clo, chi;
+        edges2(a, P0 + o_row - T::PW, alo, ahi);
+        edges2(c, P0 + o_row + T::PW, clo, chi);
+        float ga[4], gc[4];
+        xdiff(a, alo, ahi, ga);
+        xdiff(c, clo, chi, gc);
+        float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
+        {
+            // x+2 / x-2 neighbours of the quad as pairs
+            const float2 hi0 = make_float2(C0[2], C0[3]), hi1 = make_float2(E0[2], E0[3]);
+            const float2 lo0 = make_float2(E0[0], E0[1]), lo1 = make_float2(C0[0], C0[1]);
+            Hxx[0] = DD(hi0, lo1, lo0);          // voxels 0, 1: centre = (C0[0], C0[1])
+            Hxx[1] = DD(hi1, hi0, lo1);          // voxels 2, 3: centre = (C0[2], C0[3])
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int j = 2 * g;
+            const float2 f0 = PAIR(C0, j);
+            Hyy[g] = DD(PAIR(u2, j), f0, PAIR(t2, j));
+            Hzz[g] = DD(PAIR(Cp2, j), f0, PAIR(Cm2, j));
+            Hxy[g] = vmul(vsub(PAIR(gc, j), PAIR(ga, j)), qs2);
+            Hxz[g] = vmul(vsub(PAIR(Gp1, j), PAIR(Gm1, j)), qs2);
+            Hyz[g] = vmul(vsub(vsub(PAIR(nd, j), PAIR(nu, j)), vsub(PAIR(md, j), PAIR(mu, j))), qs2);
+        }
+        bool surv[4];
+        test(Hxx, Hyy, Hzz, surv);
+        unsigned slot[4];
+        slots(surv, slot);
+        append(surv, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz, slot);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) E0[k] = E1[k];
+        have = true;
+    };
+#undef PAIR
+#undef DD
+    // phase A of a plane next to a z face: the general second differences (at most four planes of a volume)
+    auto phase_a_general = [&](int z) {
+        RingField f;
+        f.ring = ring; f.o0 = tr.o[0]; f.o1 = tr.o[1]; f.o2 = tr.o[2]; f.o3 = tr.o[3]; f.o4 = tr.o[4];
+        f.zc = z; f.xb = x0; f.yb = y0; f.w = w; f.h = h; f.l = l;
+        bool surv[4] = { false, false, false, false };
+        float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            typedef Lanes<float2> L2;
+            Hess H = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+            if (m[j]) H = hessian_at_face(f, xq + j, yrow, z, p.k.sigma2);
+            L2::set(Hxx[j >> 1], j & 1, H.xx); L2::set(Hxy[j >> 1], j & 1, H.xy); L2::set(Hxz[j >> 1], j & 1, H.xz);
+            L2::set(Hyy[j >> 1], j & 1, H.yy); L2::set(Hyz[j >> 1], j & 1, H.yz); L2::set(Hzz[j >> 1], j & 1, H.zz);
+        }
+        test(Hxx, Hyy, Hzz, surv);
+        unsigned slot[4];
+        slots(surv, slot);
+        append(surv, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz, slot);
+        have = false;
+    };
+
+    // Phase B on entries [first, first + count) (ring positions, first even): PAIRS packed pairs per thread
+    auto drain = [&](unsigned first, int count) {
+#pragma unroll (Q::DRAIN_UNROLL)
+        for (int q = 0; q < Q::PAIRS; ++q) {
+            const int o = 2 * (tid + q * T::NT);           // entries o, o + 1 of the batch
+            if (o >= count) continue;
+            const bool two = o + 1 < count;
+            const float* e0 = qf + ((first + o) & (Q::CAP - 1));
+            float2 f[Q::FIELDS];
+#pragma unroll
+            for (int k = 0; k < Q::FIELDS; ++k) f[k] = *reinterpret_cast<const float2*>(e0 + k * Q::CAP);
+            // the stored responses: in flight during the eigen stage
+            long long idx[2];
+            float jold[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int pos = __float_as_int(k ? f[6].y : f[6].x);   // (z - zs) << 10 | row << 7 | column
+                const int x = bx * T::TX + (pos & 127), y = by * T::TY + ((pos >> 7) & 7), z = zs + (pos >> 10);
+                idx[k] = ((long long)(z - p.z_begin) * h + y) * w + x;
+                jold[k] = (k == 0 || two) ? __ldg(p.J + idx[k]) : 3.4e38f;
+            }
+            Eig3x2 e;
+            eig_sym3<float2, true>(f[0], f[1], f[2], f[3], f[4], f[5], e);
+            const float2 v = vesselness<float2, true>(e, p.k);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float vk = k ? v.y : v.x;
+                if (vk > jold[k]) {
+                    const long long i = idx[k];
+                    p.J[i] = vk;
+                    p.Vx[i] = (uint8_t)dir_code(k ? e.vx.y : e.vx.x);
+                    p.Vy[i] = (uint8_t)dir_code(k ? e.vy.y : e.vy.x);
+                    p.Vz[i] = (uint8_t)dir_code(k ? e.vz.y : e.vz.x);
+                    if (p.scale_idx) p.scale_idx[i] = (uint8_t)p.scale;
+                    if (p.dir) {
+                        p.dir[i] = k ? e.vx.y : e.vx.x;
+                        p.dir[p.voxels + i] = k ? e.vy.y : e.vy.x;
+                        p.dir[2 * p.voxels + i] = k ? e.vz.y : e.vz.x;
+                    }
+                    vmax = fmaxf(vmax, vk);
+                }
+            }
+        }
+    };
+
+    int rot = 0;
+    for (int z = zs; z < ze; ++z) {
+        __syncthreads();                          // nobody reads plane z-3's slot or drains any more
+        if (tid == 0 && z + PF < ze) tr.issue(&p.tmap, x0, y0, z + 2 + PF, p.f.base, l);   // into that slot
+        tr.wait_next();                           // plane z+2 has landed
+        // ---- phase A: second differences, the diagonal-sum test, survivors appended ----
+        if (z < 2 || z > l - 3) phase_a_general(z);
+        else switch (rot) {
+            case 0: phase_a(IntC<0>()); break;
+            case 1: phase_a(IntC<1>()); break;
+            case 2: phase_a(IntC<2>()); break;
+            case 3: phase_a(IntC<3>()); break;
+            default: phase_a(IntC<4>()); break;
+        }
+        rot = rot == 4 ? 0 : rot + 1;
+        pos0 += 1 << 10;
+        tr.rotate();
+        __syncthreads();                          // appended entries and the tail are visible
+        // ---- phase B: full batches from the head of the queue (everything after the last plane) ----
+        const unsigned tail = *reinterpret_cast<volatile unsigned*>(s_tail);
+        const bool flush = z + 1 == ze;
+        while (tail - head >= (unsigned)Q::BATCH || (flush && tail != head)) {
+            const int take = (int)min(tail - head, (unsigned)Q::BATCH);
+            drain(head, take);
+            head += take;
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
+    if (tx == 0 && vmax > 0.0f) atomicMax(p.minmax + 1, __float_as_int(vmax));
+}
+#else   // K3C_V1: the first form (26 row segments per quad from shared memory, stored response streamed), kept for A/B timing
 struct HessTileC {                               // tile of the compacting kernel: 128 x 8, one row per warp
     static constexpr int TX = 128, TY = 8, NT = 256;
     static constexpr int PW = HessTile::PW;      // same row pitch as HessTile (quad_hessians relies on it)
     static constexpr int PH = TY + 4;
     static constexpr int PLANE = PW * PH;        // 1584 floats: the TMA box
     static constexpr int SLOT = (PLANE * 4 + 127) / 128 * 32;   // 1600 floats
-    static constexpr int SLOTS = 6;
+    static constexpr int SLOTS = K3C_SLOTS;
     static constexpr int RING_BYTES = SLOTS * SLOT * 4;    // 38400
+    static constexpr int X_FIRST = 2;            // tile bx covers the voxels x = X_FIRST + TX * bx + [0, TX)
 };
 struct HessQueue {
     static constexpr int PAIRS = 2;                                  // packed pairs per thread per drain (ILP)
@@ -1462,6 +1814,8 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     for (int s = 16; s > 0; s >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
     if (tx == 0 && vmax > 0.0f) atomicMax(p.minmax + 1, __float_as_int(vmax));
 }
+
+#endif  // K3C_V1
 
 // K3b: the shell.  Thread index -> region: z faces (whole planes), then y faces
 // (rows of the own planes), then x faces (columns of the own planes).  Edges

@@ -113,3 +113,15 @@ void Frangi::imdilate(unsigned char* I, int w, int h, int l, float rad)
     const int rc = frangi_gpu_imdilate(I, w, h, l, rad, 0);
     if (rc) raise("frangi_gpu_imdilate", rc);
 }
+
+void Frangi::imgaussian(unsigned char* I, int w, int h, float sig_, float* F)
+{
+    const int rc = frangi_gpu_imgaussian2d(I, w, h, sig_, F, 0);
+    if (rc) raise("frangi_gpu_imgaussian2d", rc);
+}
+
+void Frangi::imerode(unsigned char* I, int w, int h, int l, float rad, float zdist_, unsigned char* E)
+{
+    const int rc = frangi_gpu_imerode_z(I, w, h, l, rad, zdist_, E, 0);
+    if (rc) raise("frangi_gpu_imerode_z", rc);
+}

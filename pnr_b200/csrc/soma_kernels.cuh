@@ -35,6 +35,23 @@ morph_pass_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int
     }
 }
 
+// z pass of the z-scaled erosion Frangi::imerode(I,w,h,l,rad,zdist,E) (frangi.cpp:971-1108): minimum over
+// [z - Lz, z + Lz] clamped to the volume, Lz = ceil(rad / zdist); one thread per (x, y) column and plane
+__global__ void __launch_bounds__(256)
+morph_min_z_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int w, int h, int l, int Lz)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w) return;
+    const long long plane = (long long)w * h;
+    const uint8_t* col = in + (long long)y * w + x;
+    for (int z = blockIdx.z; z < l; z += gridDim.z) {
+        int v = __ldg(col + z * plane);
+        for (int k = -Lz; k <= Lz; ++k) v = min(v, (int)__ldg(col + clampi(z + k, 0, l - 1) * plane));
+        out[z * plane + (long long)y * w + x] = (uint8_t)v;
+    }
+}
+
 // x pass of the in-place Gaussian: uint8 -> float32, ascending taps from zero, separately rounded (frangi.cpp:806-838)
 __global__ void __launch_bounds__(256)
 gauss_x_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ K, int w, int h, long long planes, int L, int Lt,

@@ -74,7 +74,9 @@ SYMBOLS = {
     "frangi_gpu_frangi2d": (C.c_int, [_VP, C.c_int, C.c_int, _f32p, C.c_int, C.c_float, C.c_float, C.c_int, _VP, _f32p, _f32p,
                                       _VP, _VP, _VP, C.c_int, C.c_uint]),
     "frangi_gpu_hessian2d": (C.c_int, [_VP, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP, C.c_int, C.c_uint]),
+    "frangi_gpu_imgaussian2d": (C.c_int, [_VP, C.c_int, C.c_int, C.c_float, _VP, C.c_int]),
     "frangi_gpu_imerode": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, _VP, C.c_int]),
+    "frangi_gpu_imerode_z": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _VP, C.c_int]),
     "frangi_gpu_imdilate": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]),
     "frangi_gpu_imgaussian_xy": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]),
     "frangi_gpu_host_alloc": (_VP, [C.c_size_t]),
@@ -407,6 +409,24 @@ def imerode(I, rad, device=0):
     out = np.empty_like(I)
     _check(load_library().frangi_gpu_imerode(_ptr(I), w, h, l, rad, _ptr(out), device))
     return out
+
+
+def imerode_z(I, rad, zdist, device=0):
+    """Frangi::imerode(I,w,h,l,rad,zdist,E) (frangi.h:46): the xy minimum followed by the minimum along z over
+    ceil(rad/zdist) planes each side."""
+    I, w, h, l = _vol(I)
+    out = np.empty_like(I)
+    _check(load_library().frangi_gpu_imerode_z(_ptr(I), w, h, l, rad, zdist, _ptr(out), device))
+    return out
+
+
+def imgaussian2d(I, sig, device=0):
+    """Frangi::imgaussian(I,w,h,sig,F) (frangi.h:44), the 2-D overload on an image [h][w]."""
+    I = np.ascontiguousarray(I, np.uint8)
+    h, w = I.shape
+    F = np.empty(I.shape, np.float32)
+    _check(load_library().frangi_gpu_imgaussian2d(_ptr(I), w, h, sig, _ptr(F), device))
+    return F
 
 
 def imdilate(I, rad, device=0):

@@ -59,3 +59,58 @@ def test_callsite_matches_oracle_and_ctypes_path(callsite, tmp_path, oracle):
     assert np.array_equal(g["J"], J) and np.array_equal(g["J8"], J8)
     for a, b in zip(V, (g["Vx"], g["Vy"], g["Vz"])):
         assert np.array_equal(a, b)
+
+
+# ---- link-completeness: every Frangi:: use of Advantra_plugin.cpp (:1727, :2346, :2432, :2438, :2488-2497) and every
+# other public member of the reference's frangi.h, compiled and linked against the shim; the host helpers are run
+# against fixtures generated from the compiled reference (tools/make_golden.py, cases C and G)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def members(tmp_path_factory):
+    if not os.path.exists(os.path.join(LIBDIR, "libfrangi_shim.so")):
+        pytest.skip("libfrangi_shim.so not built")
+    exe = str(tmp_path_factory.mktemp("cpp") / "frangi_members")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "pnr_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "cpp", "frangi_members.cpp"), "-o", exe, "-L", LIBDIR,
+                    "-lfrangi_shim", "-lfrangi_gpu", "-Wl,-rpath," + LIBDIR], check=True)
+    return exe
+
+
+def _pipe(exe, args, data):
+    r = subprocess.run([exe] + [str(a) for a in args], input=data, capture_output=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    return r.stdout
+
+
+def test_every_frangi_member_of_the_plugin_links_and_eigen_is_bit_identical(members):
+    g = np.load(os.path.join(GOLD, "case_c_eigen.npz"))
+    A = np.ascontiguousarray(g["A"], np.float64)
+    out = np.frombuffer(_pipe(members, ["eigen", len(A)], A.tobytes()), np.float64).reshape(len(A), 12)
+    assert np.array_equal(out[:, :9].reshape(-1, 3, 3), g["V"])      # columns = eigenvectors, reference's signs
+    assert np.array_equal(out[:, 9:], g["d"])                        # |d0| <= |d1| <= |d2| with its tie rules
+    # SURVEY 8c known answers
+    assert np.array_equal(out[0, 9:], [0, 0, 0]) and np.array_equal(out[0, :9].reshape(3, 3)[:, 0], [1, 0, 0])
+    assert np.array_equal(out[4, 9:], [1, -2, 3])
+
+
+def test_host_helpers_match_the_reference(members):
+    g = np.load(os.path.join(GOLD, "case_g_cold.npz"))
+    t3 = np.frombuffer(_pipe(members, ["dirs3", 90], b""), np.float32).reshape(-1, 3)
+    t2 = np.frombuffer(_pipe(members, ["dirs2", 30], b""), np.float32).reshape(-1, 3)
+    assert np.array_equal(t3, g["dirs3d"]) and np.array_equal(t2, g["dirs2d"])
+    for mode, tab, q, want in (("idx3", g["dirs3d"], g["q3"], g["idx3"]),
+                               ("idx2", g["dirs2d"], np.concatenate([g["q2"], np.zeros((len(g["q2"]), 1), np.float32)], 1),
+                                g["idx2"])):
+        data = np.int32(len(tab)).tobytes() + np.ascontiguousarray(tab, np.float32).tobytes() + \
+            np.ascontiguousarray(q, np.float32).tobytes()
+        assert np.array_equal(np.frombuffer(_pipe(members, [mode], data), np.uint8), want)
+    F = g["F"]
+    l, h, w = F.shape
+    q = np.concatenate([g["xy"].astype(np.float32), g["zq"][:, None]], 1)
+    got = np.frombuffer(_pipe(members, ["interp", w, h, l], F.tobytes() + np.ascontiguousarray(q, np.float32).tobytes()),
+                        np.float32)
+    assert np.array_equal(got, g["interp"])
+    one = np.frombuffer(_pipe(members, ["interp", w, h, 1], F[:1].tobytes() + np.float32([3, 5, 0.7]).tobytes()), np.float32)
+    assert one[0] == g["interp_plane"]

@@ -56,3 +56,35 @@ def test_gpu_helpers_reject_bad_arguments():
         pnr_b200.imgaussian_xy(I, 0.0)
     with pytest.raises(pnr_b200.FrangiGpuError):
         pnr_b200.imgaussian_xy(I, 11.0)          # tap radius 33 > the supported 30
+
+
+# ---- the two overloads no live code calls: z-scaled erosion (frangi.h:46), 2-D smoothing (frangi.h:44) ----
+GOLD_G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "case_g_cold.npz")
+
+
+def test_cold_overload_ports_match_the_golden_fixture(oracle):
+    g = np.load(GOLD_G)
+    I, rad, zdist = g["I"], float(g["rad"]), float(g["zdist"])
+    assert np.array_equal(oracle.imerode_z(I, rad, zdist), g["eroded_z"])
+    assert np.array_equal(oracle.imerode_z(I[:1], rad, zdist), g["eroded_z_plane"])     # l == 1: no z pass
+    assert np.array_equal(oracle.imgaussian2d(I[4], 2.0), g["smooth2d"])
+    assert (g["eroded_z"] <= oracle.imerode(I, rad)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,rad,zdist", [((64, 48, 9), 3.0, 2.0), ((37, 29, 5), 2.5, 1.0), ((9, 7, 1), 5.0, 2.0),
+                                             ((130, 20, 3), 4.0, 0.5)])
+def test_gpu_imerode_z_is_byte_exact(oracle, shape, rad, zdist):
+    import pnr_b200
+    from pnr_b200.frangi import imerode_z
+    I = _vol(*shape)
+    assert np.array_equal(imerode_z(I, rad, zdist), oracle.imerode_z(I, rad, zdist))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,sigma", [((96, 80), 2.0), ((37, 29), 4.0), ((515, 33), 1.5), ((2, 2), 1.0)])
+def test_gpu_imgaussian2d_is_bit_exact(oracle, shape, sigma):
+    from pnr_b200.frangi import imgaussian2d
+    w, h = shape
+    I = _vol(w, h, 1)[0]
+    assert np.array_equal(imgaussian2d(I, sigma), oracle.imgaussian2d(I, sigma))

@@ -116,6 +116,29 @@ def case_f_soma():
                         chain=ref.imgaussian_xy(ref.imerode(I, 2.0), 2.0))      # Advantra_plugin.cpp:2432,2438
 
 
+def case_g_cold():
+    """case G: the Frangi members no live code calls (frangi.h:28-31,44,46,51): z-scaled erosion, 2-D smoothing,
+    direction tables and their lookup, z interpolation."""
+    ref = Reference()
+    I = make_volume(56, 40, 10, seed=41, n_neurites=3)
+    rng = np.random.default_rng(9)
+    t3, t2 = ref.unit_directions(True, 90), ref.unit_directions(False, 30)
+    q3 = rng.normal(size=(200, 3)).astype(np.float32)
+    q3 /= np.linalg.norm(q3, axis=1, keepdims=True)
+    q2 = q3[:, :2] / np.linalg.norm(q3[:, :2], axis=1, keepdims=True)
+    F = ref.imgaussian(I, 2.0, 2.0)
+    zq = np.float32(rng.uniform(-1.5, I.shape[0] + 0.5, size=64))
+    xy = np.stack([rng.integers(0, I.shape[2], 64), rng.integers(0, I.shape[1], 64)], 1).astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "case_g_cold.npz"), I=I, rad=np.float32(3.0), zdist=np.float32(2.0),
+                        eroded_z=ref.imerode_z(I, 3.0, 2.0), eroded_z_plane=ref.imerode_z(I[:1], 3.0, 2.0),
+                        smooth2d=ref.imgaussian2d(I[4], 2.0), dirs3d=t3, dirs2d=t2, q3=q3, q2=q2,
+                        idx3=np.array([ref.direction_idx(v, t3) for v in q3], np.uint8),
+                        idx2=np.array([ref.direction_idx(v, t2) for v in q2], np.uint8),
+                        F=F, zq=zq, xy=xy,
+                        interp=np.array([ref.interpz(int(x), int(y), float(z), F) for (x, y), z in zip(xy, zq)], np.float32),
+                        interp_plane=np.float32(ref.interpz(3, 5, 0.7, F[:1])))
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"     # "2d" / "soma": only that case (others untouched)
     if which in ("all",):
@@ -124,3 +147,5 @@ if __name__ == "__main__":
         case_e_2d()
     if which in ("all", "soma"):
         case_f_soma()
+    if which in ("all", "cold"):
+        case_g_cold()
