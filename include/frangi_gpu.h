@@ -222,6 +222,13 @@ int frangi_gpu_last_timings(frangi_gpu_t* h, float* ms, int n);
  * every launch's device time; frangi_gpu_last_timings then reports the MEAN over
  * the runs recorded since this call (at most `depth`). */
 int frangi_gpu_timing_depth(frangi_gpu_t* h, int depth);
+/* Slabs the handle really uses: frangi_gpu_create gives every slab at least ceil(3 sigma_max / zdist) + 2
+ * planes, so a thin volume uses fewer devices than were passed (the results are the same). */
+int frangi_gpu_slab_count(frangi_gpu_t* h);
+/* Conditions that did not fail a call but that the caller should know about ("" when there are none):
+ * devices left unused, peer access unavailable between two devices of a local-halo handle (the halo
+ * copies are then staged through the host). */
+const char* frangi_gpu_warnings(frangi_gpu_t* h);
 /* The cudaStream_t (as void*) on which slab `slab` of the handle launches its
  * kernels, so that a caller can bracket runs with its own CUDA events. */
 void* frangi_gpu_stream(frangi_gpu_t* h, int slab);

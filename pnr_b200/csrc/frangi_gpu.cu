@@ -74,6 +74,29 @@ int fail(int code, const char* fmt, ...)
         if (_rc) return _rc;          \
     } while (0)
 
+// An NCCL group that is closed on every path: NK() returns from the middle of a group on an error, and a group left
+// open would swallow every later NCCL call of the thread (ncclCommDestroy included) -- one error must not become a hang.
+struct NcclGroup {
+    bool open = false;
+    int begin()
+    {
+        if (ncclx::api().GroupStart() != ncclx::ncclSuccess) return fail(FRANGI_GPU_ENCCL, "ncclGroupStart failed");
+        open = true;
+        return 0;
+    }
+    int end()
+    {
+        open = false;
+        const ncclx::ncclResult_t r = ncclx::api().GroupEnd();
+        if (r != ncclx::ncclSuccess)
+            return fail(FRANGI_GPU_ENCCL, "ncclGroupEnd failed: %s",
+                        ncclx::api().GetErrorString ? ncclx::api().GetErrorString(r) : "?");
+        return 0;
+    }
+    ~NcclGroup() { if (open) ncclx::api().GroupEnd(); }
+};
+
+
 // ---- tap planning (host; mirrors frangi.cpp:651-680 in float32) -------------
 #ifndef Z_TMA
 #define Z_TMA 1      // z pass by the TMA warp-stream kernel (0: the register-prefetch marching kernel)
@@ -268,6 +291,7 @@ struct frangi_gpu {
     int blackwhite = 0;
     unsigned flags = 0;
     int nslabs_total = 1;        // slabs in the whole job (all processes)
+    std::string warnings;        // conditions that do not fail a call but that the caller should know about (frangi_gpu_warnings)
     int rz_max = 0;
     std::vector<ScalePlan> scales;
     std::vector<Slab> slabs;     // slabs driven by this process
@@ -361,14 +385,16 @@ int make_tile_map(CUtensorMap* tm, float* F, int w, int h, int planes, int fpitc
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn encode = nullptr;
-    if (!encode) {
+    // fetched once, also when handles are created from several threads (a function-local static is initialised under a lock)
+    static const encode_fn encode = [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
-        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(FRANGI_GPU_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
-        encode = (encode_fn)fn;
-    }
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (encode_fn)fn;
+    }();
+    if (!encode) return fail(FRANGI_GPU_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
     const cuuint64_t dims[3] = { (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes };
     const cuuint64_t strides[2] = { (cuuint64_t)fpitch * 4, (cuuint64_t)fplane * 4 };
     const cuuint32_t box[3] = { (cuuint32_t)box_w, (cuuint32_t)box_h, 1 };
@@ -657,7 +683,11 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
     if (D) return launch_voxel_t<2>(p, nblocks, nshell, s.s_main);
     if (si == 0) return launch_voxel_t<0>(p, nblocks, nshell, s.s_main);
     if (H->blackwhite) return launch_voxel_t<1>(p, nblocks, nshell, s.s_main);
+#ifdef K3C_V1
     if (p.zchunk >= (1 << 21)) return launch_voxel_t<1, true>(p, nblocks, nshell, s.s_main);   // packed z offset has 21 bits
+#else
+    if (s.voxels >= (1LL << 32)) return launch_voxel_t<1, true>(p, nblocks, nshell, s.s_main);  // survivors carry 32-bit voxel offsets
+#endif
     // later scale of a bright-ridge run: the compacting kernel (its own 128 x 8 tiling), then the shell
     if (nblocks > 0) {
         p.ntx = (H->w - 2 - HessTileC::X_FIRST + HessTileC::TX - 1) / HessTileC::TX;   // tiles cover x up to w-3
@@ -722,7 +752,8 @@ int exchange_halos(frangi_gpu* H, int halo)
     if (H->local_halo) return exchange_halos_local(H, halo);
     auto& N = ncclx::api();
     const size_t plane = (size_t)H->fplane;
-    NK(N.GroupStart());
+    NcclGroup group;
+    RC(group.begin());
     for (auto& s : H->slabs) {
         const bool has_lo = s.index > 0, has_hi = s.index < H->nslabs_total - 1;
         if (has_lo) {
@@ -740,7 +771,7 @@ int exchange_halos(frangi_gpu* H, int halo)
                       s.index + 1, s.comm, s.s_comm));
         }
     }
-    NK(N.GroupEnd());
+    RC(group.end());
     return 0;
 }
 
@@ -757,9 +788,10 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
         Slab& s = H->slabs[k];
         CK(cudaSetDevice(s.dev));
         s.ev_time = s.ev_all.data() + (size_t)ev_set * (kEvPerScale * S + 2);
-        s.hMinMax[0] = 0x7f7fffff;            // FLT_MAX  (frangi.cpp:176)
-        s.hMinMax[1] = (int)0xff7fffffu;      // -FLT_MAX (frangi.cpp:177)
-        CK(cudaMemcpyAsync(s.dMinMax, s.hMinMax, 2 * sizeof(int), cudaMemcpyHostToDevice, s.s_main));
+        // Jmin = FLT_MAX, Jmax = -FLT_MAX (frangi.cpp:176-177), set ON the device: the pinned pair hMinMax is only ever
+        // the target of the result copy, so back-to-back asynchronous runs cannot pick up the previous run's result
+        minmax_init_kernel<<<1, 32, 0, s.s_main>>>(s.dMinMax);
+        g_launches++;
         CK(cudaEventRecord(s.ev_time[0], s.s_main));
     }
     // Multi-slab: the xy pass of a scale on every local slab -- boundary planes first, then the halo exchange on the
@@ -905,12 +937,13 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
         }
     } else if (multi) {
         auto& N = ncclx::api();
-        NK(N.GroupStart());
+        NcclGroup group;
+        RC(group.begin());
         for (auto& s : H->slabs) {
             NK(N.AllReduce(s.dMinMax, s.dMinMax, 1, ncclx::ncclInt32, ncclx::ncclMin, s.comm, s.s_main));
             NK(N.AllReduce(s.dMinMax + 1, s.dMinMax + 1, 1, ncclx::ncclInt32, ncclx::ncclMax, s.comm, s.s_main));
         }
-        NK(N.GroupEnd());
+        RC(group.end());
     }
     for (auto& s : H->slabs) {
         CK(cudaSetDevice(s.dev));
@@ -1038,12 +1071,13 @@ int run_streamed(frangi_gpu* H, const uint8_t* I_host, float* J, uint8_t* Vx, ui
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         s.ev_chunk.push_back(e);
     }
-    H->runs_recorded++;
+    // a streamed run records only the first / last event of set 0; the per-class sets start afresh with the next
+    // resident run, so collect() never reads an event that was not recorded
+    H->runs_recorded = 0;
     H->last_streamed = true;
     s.ev_time = s.ev_all.data();
-    s.hMinMax[0] = 0x7f7fffff;
-    s.hMinMax[1] = (int)0xff7fffffu;
-    CK(cudaMemcpyAsync(s.dMinMax, s.hMinMax, 2 * sizeof(int), cudaMemcpyHostToDevice, s.s_main));
+    minmax_init_kernel<<<1, 32, 0, s.s_main>>>(s.dMinMax);    // see run_pipeline
+    g_launches++;
     CK(cudaEventRecord(s.ev_time[0], s.s_main));
     int uploaded = s.zb;                      // planes [zb, uploaded) of the input are on their way
     for (int c = 0; c < nch; ++c) {
@@ -1155,6 +1189,12 @@ FRANGI_API int frangi_gpu_create(frangi_gpu_t** out, const float* sigmas, int ns
     // a neighbour must be able to supply a whole halo: slab thickness >= rz_max + 2
     const int min_thick = H->rz_max + 2;
     int nuse = std::min(ndev, std::max(1, l / min_thick));
+    if (nuse < ndev) {       // not an error (the result is the same), but the caller asked for more devices than are used
+        char buf[160];
+        snprintf(buf, sizeof buf, "%d of the %d devices are used: a slab must hold at least %d planes and the volume has %d; ",
+                 nuse, ndev, min_thick, l);
+        H->warnings += buf;
+    }
     H->nslabs_total = nuse;
     H->slabs.resize(nuse);
     // one slab, several scales, TMA z pass available for every radius: the overlapped schedule (run_pipeline)
@@ -1181,9 +1221,19 @@ FRANGI_API int frangi_gpu_create(frangi_gpu_t** out, const float* sigmas, int ns
                 if (devs[a] != devs[b]) {
                     e = cudaSetDevice(devs[a]);
                     if (e == cudaSuccess) {
-                        const cudaError_t pe = cudaDeviceEnablePeerAccess(devs[b], 0);
-                        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-                        else if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                        int can = 0;
+                        e = cudaDeviceCanAccessPeer(&can, devs[a], devs[b]);
+                        if (e != cudaSuccess) break;
+                        cudaError_t pe = can ? cudaDeviceEnablePeerAccess(devs[b], 0) : cudaErrorPeerAccessUnsupported;
+                        if (pe == cudaErrorPeerAccessAlreadyEnabled) pe = cudaSuccess;
+                        if (pe != cudaSuccess) {
+                            // the halo pulls still work (staged through the host) but are far slower: say so
+                            char buf[160];
+                            snprintf(buf, sizeof buf, "no peer access from device %d to device %d: halo copies are staged through the host; ",
+                                     devs[a], devs[b]);
+                            H->warnings += buf;
+                        }
+                        cudaGetLastError();
                     }
                 }
         if (e != cudaSuccess) rc = fail(FRANGI_GPU_ECUDA, "local halo setup: %s", cudaGetErrorString(e));
@@ -1361,6 +1411,10 @@ FRANGI_API int frangi_gpu_timing_depth(frangi_gpu_t* H, int depth)
     H->runs_recorded = 0;
     return 0;
 }
+
+FRANGI_API int frangi_gpu_slab_count(frangi_gpu_t* H) { return H ? (int)H->slabs.size() : 0; }
+
+FRANGI_API const char* frangi_gpu_warnings(frangi_gpu_t* H) { return H ? H->warnings.c_str() : ""; }
 
 FRANGI_API void* frangi_gpu_stream(frangi_gpu_t* H, int slab)
 {

@@ -640,7 +640,7 @@ struct TileRing {
 #endif
 struct ZTile {
     static constexpr int COLS = 128, DEPTH = ZT_DEPTH, WARPS = ZT_WARPS;   // a lane owns 4 adjacent columns
-    static constexpr int SMEM_BYTES = WARPS * (DEPTH * (COLS * 4 + 8) + 128);   // rings, barriers, one scratch word per lane
+    static constexpr int SMEM_BYTES = WARPS * DEPTH * (COLS * 4 + 16);          // rings, one full and one empty mbarrier per slot
 };
 
 template <int LZ, bool EXACT>
@@ -664,10 +664,11 @@ gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     const float* ring = zring + warp * D * ZTile::COLS;
     const uint32_t ring_s = smem_u32(ring);
     const uint32_t bar_s = smem_u32(zring + ZTile::WARPS * D * ZTile::COLS) + warp * D * 8;
-    const uint32_t scratch_s = smem_u32(zring + ZTile::WARPS * D * ZTile::COLS) + ZTile::WARPS * D * 8 + warp * 128 + lane * 4;
+    // one "empty" mbarrier per slot next to the "full" one: the consumer-release half of the producer / consumer pair
+    const uint32_t empty_s = smem_u32(zring + ZTile::WARPS * D * ZTile::COLS) + ZTile::WARPS * D * 8 + warp * D * 8;
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) mbar_init(bar_s + 8 * k, 1);
+        for (int k = 0; k < D; ++k) { mbar_init(bar_s + 8 * k, 1); mbar_init(empty_s + 8 * k, 32); }
         mbar_init_fence();
     }
     __syncwarp();
@@ -689,14 +690,17 @@ gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     auto next = [&](int j) {                                   // input j of the chunk, this lane's four columns
         mbar_wait(bar_s + 8 * slot, par);
         const float4 v = *reinterpret_cast<const float4*>(ring + slot * ZTile::COLS + 4 * lane);
-        // The slot may be refilled only after the shared-memory load has DELIVERED: the load is asynchronous to the
-        // instruction stream (its result is first needed many instructions later), and a refill that is served from
-        // L2 can land while a quarter-warp of the load is still queued in the memory pipeline -- seen as rare 16-byte
-        // corruptions when NCCL kernels ran beside this one.
-        // A store of the loaded value cannot issue before the load has delivered and stays ahead of the copy below.
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch_s), "f"(v.w) : "memory");
-        __syncwarp();                                          // every lane has its copy
-        if (lane == 0 && j + D < nin) issue();
+        // Slot reuse is ordered by the standard full / empty barrier pair: every lane ARRIVES on the slot's empty
+        // barrier after its load (the arrive has release semantics: the load is performed before the arrival is
+        // observed) and lane 0 WAITS for all 32 arrivals before it arms the full barrier and issues the refill.
+        // A refill that is merely issued after the load INSTRUCTION can land, served from L2, while a quarter-warp
+        // of the load is still queued in the memory pipeline -- seen as rare 16-byte corruptions when NCCL kernels
+        // ran beside this one (round 1; then closed with a dependent dummy store, now with the documented pattern).
+        mbar_arrive(empty_s + 8 * slot);
+        if (lane == 0 && j + D < nin) {
+            mbar_wait(empty_s + 8 * slot, par);                // use k of the slot completes phase k of both barriers
+            issue();
+        }
         if (++slot == D) { slot = 0; par ^= 1u; }
         return v;
     };
@@ -1270,50 +1274,50 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
 #define K3C_DRAIN_UNROLL 1
 #endif
 #ifndef K3C_V1
-// ---- K3a' (current form) ------------------------------------------------------------------------------------
-// The first form (below, -DK3C_V1) read every quad's 26 row segments of the five planes from shared memory per
-// plane: 133 shared-memory wavefronts per warp and plane, which is what bounded it (the shared-memory pipe was 87 %
-// busy during phase A; profiles/r1n).  Testing the diagonal first and fetching the rest only for quads with a
-// survivor does not help: the survivors are noise voxels, spread evenly (57 % of the quads hold one).  This form cuts
-// the traffic itself:
-//  * tiles are 16-byte aligned with the quads (the box starts 4 columns left of the tile), so a row segment of a
-//    quad is ONE 128-bit load with a lane stride of 16 bytes -- 4 wavefronts for 512 useful bytes, where the
-//    2-column offset of the first form needed two 64-bit loads (8 wavefronts);
-//  * the columns next to a quad (x-2, x-1, x+4, x+5) come from the neighbour lanes' registers by warp shuffle
-//    (lanes 0 and 31 take them from the tile's halo columns);
-//  * a thread keeps its own row of the planes z-2 .. z+2 and the x first differences of the planes z-1 .. z+1 in
-//    register rings (the z window marches with the thread), rotated by renaming: the plane loop dispatches on
-//    (z mod 5) to five instantiations of phase A whose register indices are static.
-// Per quad and plane: 9 aligned 128-bit loads (own row of plane z+2; rows y-1, y+1 of planes z-1, z, z+1; rows
-// y-2, y+2 of plane z), 8 shuffles and 3 single-lane halo loads = 48 wavefronts instead of 133.
-// The stored response J of a survivor is fetched at the drain (a gather over the ~20 % of the voxels that reach
-// it) instead of being streamed for every voxel.  Same operations on the same operands in the same order as
-// quad_hessians<false>: bit-identical second differences.
-struct HessTileC {                               // 128 x 8 voxels, one row per warp, one quad per thread
-    static constexpr int TX = 128, TY = 8, NT = 256;
-    static constexpr int XH = 4;                 // box columns left / right of the tile (16-byte aligned quads)
-    static constexpr int PW = TX + 2 * XH;       // 136 floats per tile row
+// ---- K3a' (current form): warp-autonomous streaming, mbarrier full / empty tile ring, per-warp survivor queues ----
+// History (profiles/r2*): the first form (below, -DK3C_V1) read every quad's 26 row segments of the five planes from
+// shared memory per plane and ran phase A / phase B in CTA-wide lock step (two __syncthreads per plane, one shared
+// survivor queue): 13.4 ms per launch at 2048 x 2048 x 512, 48 % issue utilisation.  Testing the diagonal first
+// and fetching the rest only for quads with a survivor did not help (survivors are noise voxels, spread evenly: 57 %
+// of the quads hold one); halving the shared-memory wavefronts (aligned tiles + shuffles) did not help either: the
+// kernel is bound by instruction count and by the lock step (stall reasons: fixed-latency wait, barrier), not by a
+// single pipe.  This form attacks both:
+//  * a WARP owns one tile row and marches along z on its own: the tile ring is filled by TMA and guarded by a
+//    full (transaction) and an empty (consumer release, 256 arrivals) mbarrier per slot -- no __syncthreads in
+//    the plane loop; slot s is refilled by lane 0 of warp s once every warp has released it, so warps may drift a
+//    few planes apart and the eigen stage of one warp overlaps the second differences of another;
+//  * each warp has its own survivor queue (no shared counter, no atomics): slots come from ballots, a drain runs
+//    whenever the warp has 64 survivors (one packed pair per lane);
+//  * tiles are 16-byte aligned with the quads: a row segment of a quad is ONE 128-bit load with a lane stride of
+//    16 bytes, the columns next to a quad come from the neighbour lanes by shuffle, and lanes 0 / 31 only carry
+//    the halo (a tile is 120 columns wide), so there is no edge-lane special case at all;
+//  * a lane keeps its own row of the planes z-2 .. z+2 and the x first differences of z-1 .. z+1 in register
+//    rings rotated by renaming (the plane loop dispatches on z mod 5 to five instantiations of phase A);
+//  * survivors carry their 32-bit linear voxel offset; the stored response is gathered at the drain.
+// Same operations on the same operands in the same order as quad_hessians<false>: bit-identical second differences.
+struct HessTileC {                               // 120 x 8 voxels: one row per warp, one quad per lane, lanes 0 / 31 halo only
+    static constexpr int TX = 120, TY = 8, NT = 256;
+    static constexpr int XH = 4;                 // halo columns each side (one quad)
+    static constexpr int PW = TX + 2 * XH;       // 128 floats per tile row
     static constexpr int PH = TY + 4;
-    static constexpr int PLANE = PW * PH;        // 1632 floats: the TMA box
-    static constexpr int SLOT = (PLANE * 4 + 127) / 128 * 32;   // 1632 floats (6528 bytes)
-    static constexpr int SLOTS = K3C_SLOTS;      // planes z-2 .. z+2 in use + SLOTS - 5 planes in flight
+    static constexpr int PLANE = PW * PH;        // 1536 floats: the TMA box
+    static constexpr int SLOT = PLANE;           // 6144 bytes (a multiple of 128)
+    static constexpr int SLOTS = 8;              // = warps: warp s refills slot s
     static constexpr int RING_BYTES = SLOTS * SLOT * 4;
     static constexpr int X_FIRST = 0;            // tile bx covers the voxels x = TX * bx + [0, TX); x = 0, 1 are masked (shell)
+#ifndef K3C_AHEAD
+#define K3C_AHEAD 6
+#endif
+    static constexpr int AHEAD = K3C_AHEAD;      // plane sequence number n is issued at iteration >= n - AHEAD (n = z + 2 at AHEAD 4)
 };
-struct HessQueue {
-    static constexpr int PAIRS = 2;                                  // packed pairs per thread per drain
-    static constexpr int BATCH = 2 * PAIRS * HessTileC::NT;          // 1024 entries per drain
-    static constexpr int APPEND = HessTileC::TX * HessTileC::TY;     // most one plane can add (1024)
-    // Appends only happen right after the plane barrier, when at most BATCH - 1 entries are pending and no drain is
-    // in flight, so BATCH + APPEND ring entries can never collide; a power of two so that the ring index is a mask.
-    static constexpr int CAP = 2048;
-    static_assert(CAP >= BATCH + APPEND, "queue too small");
-    // structure of arrays: field f of entry e at float f * CAP + e; fields = Dxx, Dxy, Dxz, Dyy, Dyz, Dzz, packed position.
-    // A drain reads entries (e, e + 1), e even, as one 64-bit load per field: the packed register pair of the eigen stage.
+struct HessQueue {                               // per warp
+    static constexpr int BATCH = 64;             // one packed pair per lane
+    static constexpr int CAP = 256;              // power of two >= BATCH - 1 + the 120 entries one plane can add
+    // structure of arrays: field f of entry e at float f * CAP + e; fields = Dxx, Dxy, Dxz, Dyy, Dyz, Dzz, linear voxel offset
     static constexpr int FIELDS = 7;
-    static constexpr int DRAIN_UNROLL = K3C_DRAIN_UNROLL;            // 1: the pairs of a drain go through the eigen stage one after the other (registers)
-    static constexpr int BYTES = CAP * FIELDS * 4;
-    static constexpr int SMEM_BYTES = HessTileC::RING_BYTES + BYTES + HessTileC::SLOTS * 8 + 16;   // + mbarriers + tail counter
+    static constexpr int WARP_FLOATS = FIELDS * CAP;
+    static constexpr int BYTES = (HessTileC::NT / 32) * WARP_FLOATS * 4;
+    static constexpr int SMEM_BYTES = HessTileC::RING_BYTES + BYTES + 2 * HessTileC::SLOTS * 8;   // + full and empty mbarriers
 };
 
 template <int N> struct IntC { static constexpr int value = N; };
@@ -1332,17 +1336,37 @@ struct RingField {
     }
 };
 
+// seven predicated 32-bit shared stores of one queue entry (no branch)
+__device__ __forceinline__ void queue_append7(uint32_t addr, bool pred, float d0, float d1, float d2, float d3, float d4,
+                                              float d5, uint32_t off)
+{
+    constexpr int S = HessQueue::CAP * 4;          // byte stride between the field arrays
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "@p st.shared.f32 [%0], %2;\n\t"
+        "@p st.shared.f32 [%0 + %9], %3;\n\t"
+        "@p st.shared.f32 [%0 + %10], %4;\n\t"
+        "@p st.shared.f32 [%0 + %11], %5;\n\t"
+        "@p st.shared.f32 [%0 + %12], %6;\n\t"
+        "@p st.shared.f32 [%0 + %13], %7;\n\t"
+        "@p st.shared.b32 [%0 + %14], %8;\n\t}"
+        ::"r"(addr), "r"((uint32_t)pred), "f"(d0), "f"(d1), "f"(d2), "f"(d3), "f"(d4), "f"(d5), "r"(off),
+          "n"(S), "n"(2 * S), "n"(3 * S), "n"(4 * S), "n"(5 * S), "n"(6 * S) : "memory");
+}
+
 __global__ void __launch_bounds__(HessTileC::NT, 2)
 hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
 {
     using T = HessTileC;
     using Q = HessQueue;
     extern __shared__ __align__(128) float ring[];
-    float* qf = ring + T::SLOTS * T::SLOT;                                 // FIELDS arrays of CAP floats
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(qf + Q::FIELDS * Q::CAP);
-    unsigned* s_tail = reinterpret_cast<unsigned*>(mbar + T::SLOTS);       // entries ever appended (ring index = tail % CAP)
     const int tid = threadIdx.x;
-    const int tx = tid & 31, ty = tid >> 5;
+    const int tx = tid & 31, wid = tid >> 5;
+    float* qw = ring + T::SLOTS * T::SLOT + wid * Q::WARP_FLOATS;          // this warp's queue
+    const uint32_t full_s = smem_u32(ring + T::SLOTS * T::SLOT + (T::NT / 32) * Q::WARP_FLOATS);
+    const uint32_t empty_s = full_s + 8 * T::SLOTS;
+    const uint32_t ring_s = smem_u32(ring);
     int bid = blockIdx.x;
     const int bx = bid % p.ntx; bid /= p.ntx;
     const int by = bid % p.nty;
@@ -1352,103 +1376,93 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     const int zs = p.z_begin + bz * p.zchunk;
     const int ze = min(zs + p.zchunk, p.z_begin + p.nz);
     if (zs >= ze) return;
-    if (tid == 0) *s_tail = 0;
+    const int nz = ze - zs;
+    const int nseq = nz + 4;                      // plane sequence numbers: n <-> plane zs - 2 + n, slot n % 8, phase n / 8
 
-    TileRing<T> tr;
-    tr.init(ring, mbar, tid);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < T::SLOTS; ++k) { mbar_init(full_s + 8 * k, 1); mbar_init(empty_s + 8 * k, T::NT); }
+        mbar_init_fence();
+    }
     __syncthreads();
-    constexpr int PF = T::SLOTS - 5;              // planes in flight beyond z+2
-    if (tid == 0)
-        for (int q = zs - 2; q <= min(zs + 1 + PF, ze + 1); ++q) tr.issue(&p.tmap, x0, y0, q, p.f.base, l);
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) tr.wait_next();
+    // lane 0 of warp s: start the copy of plane sequence number n (n % 8 == s) into slot s
+    auto issue = [&](int n) {
+        const int plane = zs - 2 + n;
+        const uint32_t bar = full_s + 8 * wid;
+        if (plane < 0 || plane > l - 1) mbar_arrive(bar);          // beyond a z face: never read, but the phase completes
+        else {
+            mbar_expect_tx(bar, T::PLANE * 4);
+            tma_load_3d(ring_s + wid * (T::SLOT * 4), &p.tmap, bar, x0, y0, plane - p.f.base);
+        }
+    };
+    int next_n = wid;                             // lane 0: the next sequence number this warp issues
+    if (tx == 0 && next_n < nseq) { issue(next_n); next_n += T::SLOTS; }
 
-    const int xq = bx * T::TX + 4 * tx;           // first voxel of the quad
-    const int yl = ty;                            // one tile row per warp
-    const int yrow = by * T::TY + yl;
-    const bool row_ok = yrow >= 2 && yrow <= h - 3;
-    bool m[4];                                    // voxel j of the quad is an interior voxel
+    const int xq = x0 + 4 * tx;                   // first voxel of the lane's quad (lanes 0 and 31: halo only)
+    const int yrow = by * T::TY + wid;            // the warp's row
+    const bool row_ok = yrow >= 2 && yrow <= h - 3 && tx >= 1 && tx <= 30;
+    bool m[4];                                    // voxel j of the quad is an interior voxel of this tile
 #pragma unroll
     for (int j = 0; j < 4; ++j) m[j] = row_ok && xq + j >= 2 && xq + j <= w - 3;
-    float vmax = 0.0f;
-    unsigned head = 0;        // entries [head, tail) are pending; every thread carries the same value
-    const int o_own = (yl + 2) * T::PW + T::XH + 4 * tx;      // tile entry of (xq, yrow)
-    const int o_row = (yl + 2) * T::PW;                       // tile entry 0 of the warp's row
-    int pos0 = (yl << 7) | (4 * tx);              // + (z - zs) << 10
+    const int o_own = (wid + 2) * T::PW + 4 * tx; // tile entry of (xq, yrow)
     const float qs = 0.25f * p.k.sigma2;
     const float2 qs2 = make_float2(qs, qs);
     const unsigned below = (1u << tx) - 1u;
-    const bool edge_lane = tx == 0 || tx == 31;
+    const unsigned plane_vox = (unsigned)(h * w);                          // own voxels < 2^32 (checked by the host)
+    unsigned off0 = (unsigned)(((long long)(zs - p.z_begin) * h + yrow) * w + xq);   // linear offset of (xq, yrow, z) in the own-plane outputs
+    const uint32_t qw_s = smem_u32(qw);
+    unsigned head = 0, tail = 0;                  // this warp's queue: entries [head, tail) pending (warp-uniform)
+    float vmax = 0.0f;
 
     // Register rings (slot (rot + k) % 5 holds plane z-2+k): C = the quad's own row, G = its x first differences
     // F[x+1] - F[x-1] (planes z-1 .. z+1 live).  E0 = the columns x-2, x-1, x+4, x+5 of plane z.
     float C[5][4], G[5][4], E0[4];
     bool have = false;        // the rings hold planes z-2 .. z+1 (and G z-1, z; E0) of the plane about to be processed
 
-    // columns x-2, x-1, x+4, x+5 of a row whose quad is c[0..3]: the neighbour lanes' registers, the tile's halo
-    // columns for lanes 0 and 31 (`rowp` = tile entry 0 of the row)
-    auto edges4 = [&](const float* c, const float* rowp, float* e) {
+    auto edges4 = [&](const float* c, float* e) {          // columns x-2, x-1, x+4, x+5 from the neighbour lanes
         e[0] = __shfl_up_sync(0xffffffffu, c[2], 1); e[1] = __shfl_up_sync(0xffffffffu, c[3], 1);
         e[2] = __shfl_down_sync(0xffffffffu, c[0], 1); e[3] = __shfl_down_sync(0xffffffffu, c[1], 1);
-        if (edge_lane) {
-            const float2 v = *reinterpret_cast<const float2*>(rowp + (tx ? T::XH + T::TX : T::XH - 2));
-            if (tx) { e[2] = v.x; e[3] = v.y; } else { e[0] = v.x; e[1] = v.y; }
-        }
     };
-    // columns x-1, x+4 only
-    auto edges2 = [&](const float* c, const float* rowp, float& lo, float& hi) {
-        lo = __shfl_up_sync(0xffffffffu, c[3], 1);
-        hi = __shfl_down_sync(0xffffffffu, c[0], 1);
-        if (edge_lane) {
-            const float v = rowp[tx ? T::XH + T::TX : T::XH - 1];
-            if (tx) hi = v; else lo = v;
-        }
-    };
-    // x first differences of the quad: F[x+j+1] - F[x+j-1]
-    auto xdiff = [&](const float* c, float lo, float hi, float* g) {
+    auto xdiff = [&](const float* c, float lo, float hi, float* g) {      // F[x+j+1] - F[x+j-1]
         g[0] = __fsub_rn(c[1], lo); g[1] = __fsub_rn(c[2], c[0]); g[2] = __fsub_rn(c[3], c[1]); g[3] = __fsub_rn(hi, c[2]);
+    };
+    auto xdiff_row = [&](const float* c, float* g) {        // the same for a row whose edge columns are not kept
+        xdiff(c, __shfl_up_sync(0xffffffffu, c[3], 1), __shfl_down_sync(0xffffffffu, c[0], 1), g);
     };
     auto ld4a = [&](float* d, const float* s) { *reinterpret_cast<float4*>(d) = *reinterpret_cast<const float4*>(s); };
 
-    // survivors of the quad go to the queue
-    auto append = [&](const bool* surv, const float2* Hxx, const float2* Hxy, const float2* Hxz, const float2* Hyy,
-                      const float2* Hyz, const float2* Hzz, const unsigned* slot) {
-        typedef Lanes<float2> L2;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (surv[j]) {
-                float* e = qf + (slot[j] & (Q::CAP - 1));
-                e[0] = L2::get(Hxx[j >> 1], j & 1); e[Q::CAP] = L2::get(Hxy[j >> 1], j & 1);
-                e[2 * Q::CAP] = L2::get(Hxz[j >> 1], j & 1); e[3 * Q::CAP] = L2::get(Hyy[j >> 1], j & 1);
-                e[4 * Q::CAP] = L2::get(Hyz[j >> 1], j & 1); e[5 * Q::CAP] = L2::get(Hzz[j >> 1], j & 1);
-                e[6 * Q::CAP] = __int_as_float(pos0 + j);
-            }
-    };
-    // queue slots of the quad's survivors: warp-aggregated, one shared atomic per warp and plane (convergent code)
-    auto slots = [&](const bool* surv, unsigned* slot) {
-        const unsigned b0 = __ballot_sync(0xffffffffu, surv[0]), b1 = __ballot_sync(0xffffffffu, surv[1]);
-        const unsigned b2 = __ballot_sync(0xffffffffu, surv[2]), b3 = __ballot_sync(0xffffffffu, surv[3]);
-        if ((b0 | b1 | b2 | b3) == 0u) return;
-        const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-        unsigned base = 0;
-        if (tx == 0) base = atomicAdd(s_tail, (unsigned)(n0 + n1 + n2 + n3));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        slot[0] = base + __popc(b0 & below); slot[1] = base + n0 + __popc(b1 & below);
-        slot[2] = base + n0 + n1 + __popc(b2 & below); slot[3] = base + n0 + n1 + n2 + __popc(b3 & below);
-    };
-    // the diagonal-sum test (Ky Fan): a voxel whose response can be positive has Dxx+Dyy, Dxx+Dzz, Dyy+Dzz <= 0
-    auto test = [&](const float2* Hxx, const float2* Hyy, const float2* Hzz, bool* surv) {
+    // the diagonal-sum test (Ky Fan), queue slots from ballots, survivors appended
+    auto test_append = [&](const float2* Hxx, const float2* Hxy, const float2* Hxz, const float2* Hyy, const float2* Hyz,
+                           const float2* Hzz) {
+        bool surv[4];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
             const float2 sxy = vadd(Hxx[g], Hyy[g]), sxz = vadd(Hxx[g], Hzz[g]), syz = vadd(Hyy[g], Hzz[g]);
             surv[2 * g] = m[2 * g] && fmaxf(fmaxf(sxy.x, sxz.x), syz.x) <= 0.0f;
             surv[2 * g + 1] = m[2 * g + 1] && fmaxf(fmaxf(sxy.y, sxz.y), syz.y) <= 0.0f;
         }
+        const unsigned b0 = __ballot_sync(0xffffffffu, surv[0]), b1 = __ballot_sync(0xffffffffu, surv[1]);
+        const unsigned b2 = __ballot_sync(0xffffffffu, surv[2]), b3 = __ballot_sync(0xffffffffu, surv[3]);
+        const unsigned s0 = tail + __popc(b0 & below);
+        const unsigned t1 = tail + __popc(b0);
+        const unsigned s1 = t1 + __popc(b1 & below);
+        const unsigned t2 = t1 + __popc(b1);
+        const unsigned s2 = t2 + __popc(b2 & below);
+        const unsigned t3 = t2 + __popc(b2);
+        const unsigned s3 = t3 + __popc(b3 & below);
+        tail = t3 + __popc(b3);
+        const unsigned slot[4] = { s0, s1, s2, s3 };
+        typedef Lanes<float2> L2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            queue_append7(qw_s + 4 * (slot[j] & (Q::CAP - 1)), surv[j],
+                          L2::get(Hxx[j >> 1], j & 1), L2::get(Hxy[j >> 1], j & 1), L2::get(Hxz[j >> 1], j & 1),
+                          L2::get(Hyy[j >> 1], j & 1), L2::get(Hyz[j >> 1], j & 1), L2::get(Hzz[j >> 1], j & 1), off0 + j);
     };
 #define PAIR(arr, i) make_float2((arr)[(i)], (arr)[(i) + 1])
 #define DD(hi, mid, lo) vmul(vsub(vsub(hi, mid), vsub(mid, lo)), qs2)
-    // phase A of an interior plane (2 <= z <= l-3) with the register rings at rotation R
-    auto phase_a = [&](auto rc) {
+    // phase A of an interior plane (2 <= z <= l-3) with the register rings at rotation R; Pk = ring slot of plane z+k
+    auto phase_a = [&](auto rc, const float* Pm2, const float* Pm1, const float* P0, const float* Pp1, const float* Pp2) {
         constexpr int R = decltype(rc)::value;
         float (&Cm2)[4] = C[R % 5];
         float (&Cm1)[4] = C[(R + 1) % 5];
@@ -1458,37 +1472,27 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         float (&Gm1)[4] = G[(R + 1) % 5];
         float (&G0)[4] = G[(R + 2) % 5];
         float (&Gp1)[4] = G[(R + 3) % 5];
-        const float* Pm1 = ring + tr.o[1];
-        const float* P0 = ring + tr.o[2];
-        const float* Pp1 = ring + tr.o[3];
         if (!have) {          // first plane of the chunk, or the plane after one next to a z face (warp-uniform)
-            ld4a(Cm2, ring + tr.o[0] + o_own); ld4a(Cm1, Pm1 + o_own); ld4a(C0, P0 + o_own); ld4a(Cp1, Pp1 + o_own);
-            float lo, hi;
-            edges2(Cm1, Pm1 + o_row, lo, hi);
-            xdiff(Cm1, lo, hi, Gm1);
-            edges4(C0, P0 + o_row, E0);
+            ld4a(Cm2, Pm2 + o_own); ld4a(Cm1, Pm1 + o_own); ld4a(C0, P0 + o_own); ld4a(Cp1, Pp1 + o_own);
+            xdiff_row(Cm1, Gm1);
+            edges4(C0, E0);
             xdiff(C0, E0[1], E0[2], G0);
         }
-        // every thread loads (rows beyond the volume are zero-filled tile rows): shuffles need all lanes, and ring rows
-        // written unconditionally are what lets the compiler see that a rotated-out row is dead
-        ld4a(Cp2, ring + tr.o[4] + o_own);
+        // every lane loads and shuffles (rows beyond the volume are zero-filled tile rows)
+        ld4a(Cp2, Pp2 + o_own);
         float E1[4];
-        edges4(Cp1, Pp1 + o_row, E1);
+        edges4(Cp1, E1);
         xdiff(Cp1, E1[1], E1[2], Gp1);
         float a[4], c[4], mu[4], md[4], nu[4], nd[4], t2[4], u2[4];
         ld4a(a, P0 + o_own - T::PW); ld4a(c, P0 + o_own + T::PW);
         ld4a(t2, P0 + o_own - 2 * T::PW); ld4a(u2, P0 + o_own + 2 * T::PW);
         ld4a(mu, Pm1 + o_own - T::PW); ld4a(md, Pm1 + o_own + T::PW);
         ld4a(nu, Pp1 + o_own - T::PW); ld4a(nd, Pp1 + o_own + T::PW);
-        float alo, ahi, clo, chi;
-        edges2(a, P0 + o_row - T::PW, alo, ahi);
-        edges2(c, P0 + o_row + T::PW, clo, chi);
         float ga[4], gc[4];
-        xdiff(a, alo, ahi, ga);
-        xdiff(c, clo, chi, gc);
+        xdiff_row(a, ga);
+        xdiff_row(c, gc);
         float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
         {
-            // x+2 / x-2 neighbours of the quad as pairs
             const float2 hi0 = make_float2(C0[2], C0[3]), hi1 = make_float2(E0[2], E0[3]);
             const float2 lo0 = make_float2(E0[0], E0[1]), lo1 = make_float2(C0[0], C0[1]);
             Hxx[0] = DD(hi0, lo1, lo0);          // voxels 0, 1: centre = (C0[0], C0[1])
@@ -1504,11 +1508,7 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
             Hxz[g] = vmul(vsub(PAIR(Gp1, j), PAIR(Gm1, j)), qs2);
             Hyz[g] = vmul(vsub(vsub(PAIR(nd, j), PAIR(nu, j)), vsub(PAIR(md, j), PAIR(mu, j))), qs2);
         }
-        bool surv[4];
-        test(Hxx, Hyy, Hzz, surv);
-        unsigned slot[4];
-        slots(surv, slot);
-        append(surv, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz, slot);
+        test_append(Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
 #pragma unroll
         for (int k = 0; k < 4; ++k) E0[k] = E1[k];
         have = true;
@@ -1516,11 +1516,10 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
 #undef PAIR
 #undef DD
     // phase A of a plane next to a z face: the general second differences (at most four planes of a volume)
-    auto phase_a_general = [&](int z) {
+    auto phase_a_general = [&](int z, int o0, int o1, int o2, int o3, int o4) {
         RingField f;
-        f.ring = ring; f.o0 = tr.o[0]; f.o1 = tr.o[1]; f.o2 = tr.o[2]; f.o3 = tr.o[3]; f.o4 = tr.o[4];
+        f.ring = ring; f.o0 = o0; f.o1 = o1; f.o2 = o2; f.o3 = o3; f.o4 = o4;
         f.zc = z; f.xb = x0; f.yb = y0; f.w = w; f.h = h; f.l = l;
-        bool surv[4] = { false, false, false, false };
         float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1530,42 +1529,31 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
             L2::set(Hxx[j >> 1], j & 1, H.xx); L2::set(Hxy[j >> 1], j & 1, H.xy); L2::set(Hxz[j >> 1], j & 1, H.xz);
             L2::set(Hyy[j >> 1], j & 1, H.yy); L2::set(Hyz[j >> 1], j & 1, H.yz); L2::set(Hzz[j >> 1], j & 1, H.zz);
         }
-        test(Hxx, Hyy, Hzz, surv);
-        unsigned slot[4];
-        slots(surv, slot);
-        append(surv, Hxx, Hxy, Hxz, Hyy, Hyz, Hzz, slot);
+        test_append(Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
         have = false;
     };
 
-    // Phase B on entries [first, first + count) (ring positions, first even): PAIRS packed pairs per thread
-    auto drain = [&](unsigned first, int count) {
-#pragma unroll (Q::DRAIN_UNROLL)
-        for (int q = 0; q < Q::PAIRS; ++q) {
-            const int o = 2 * (tid + q * T::NT);           // entries o, o + 1 of the batch
-            if (o >= count) continue;
+    // Phase B on this warp's entries [head, head + count), count <= 64: lane t takes entries head + 2t, head + 2t + 1
+    auto drain = [&](int count) {
+        const int o = 2 * tx;
+        if (o < count) {
             const bool two = o + 1 < count;
-            const float* e0 = qf + ((first + o) & (Q::CAP - 1));
+            const float* e0 = qw + ((head + o) & (Q::CAP - 1));                 // head is even: the pair does not wrap
             float2 f[Q::FIELDS];
 #pragma unroll
             for (int k = 0; k < Q::FIELDS; ++k) f[k] = *reinterpret_cast<const float2*>(e0 + k * Q::CAP);
+            const unsigned i0 = __float_as_uint(f[6].x), i1 = two ? __float_as_uint(f[6].y) : i0;
             // the stored responses: in flight during the eigen stage
-            long long idx[2];
-            float jold[2];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int pos = __float_as_int(k ? f[6].y : f[6].x);   // (z - zs) << 10 | row << 7 | column
-                const int x = bx * T::TX + (pos & 127), y = by * T::TY + ((pos >> 7) & 7), z = zs + (pos >> 10);
-                idx[k] = ((long long)(z - p.z_begin) * h + y) * w + x;
-                jold[k] = (k == 0 || two) ? __ldg(p.J + idx[k]) : 3.4e38f;
-            }
+            const float j0 = __ldcg(p.J + i0);
+            const float j1 = two ? __ldcg(p.J + i1) : 3.4e38f;
             Eig3x2 e;
             eig_sym3<float2, true>(f[0], f[1], f[2], f[3], f[4], f[5], e);
             const float2 v = vesselness<float2, true>(e, p.k);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const float vk = k ? v.y : v.x;
-                if (vk > jold[k]) {
-                    const long long i = idx[k];
+                if (vk > (k ? j1 : j0)) {
+                    const size_t i = k ? i1 : i0;
                     p.J[i] = vk;
                     p.Vx[i] = (uint8_t)dir_code(k ? e.vx.y : e.vx.x);
                     p.Vy[i] = (uint8_t)dir_code(k ? e.vy.y : e.vy.x);
@@ -1580,35 +1568,47 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
                 }
             }
         }
+        head += count;
     };
 
     int rot = 0;
-    for (int z = zs; z < ze; ++z) {
-        __syncthreads();                          // nobody reads plane z-3's slot or drains any more
-        if (tid == 0 && z + PF < ze) tr.issue(&p.tmap, x0, y0, z + 2 + PF, p.f.base, l);   // into that slot
-        tr.wait_next();                           // plane z+2 has landed
-        // ---- phase A: second differences, the diagonal-sum test, survivors appended ----
-        if (z < 2 || z > l - 3) phase_a_general(z);
+#pragma unroll 1
+    for (int c = 0; c < nz; ++c) {                // centre plane z = zs + c; its window = sequence numbers c .. c+4
+        const int z = zs + c;
+        // issue duty: this warp's next plane once it is within AHEAD of the window and every warp has released the slot
+        if (tx == 0) {
+            while (next_n < nseq && next_n <= c + T::AHEAD) {
+                mbar_wait(empty_s + 8 * wid, (unsigned)((next_n >> 3) - 1) & 1u);
+                issue(next_n);
+                next_n += T::SLOTS;
+            }
+        }
+        __syncwarp();
+        if (c == 0) {
+#pragma unroll 1
+            for (int n = 0; n < 4; ++n) mbar_wait(full_s + 8 * n, 0u);
+        }
+        mbar_wait(full_s + 8 * ((c + 4) & 7), (unsigned)((c + 4) >> 3) & 1u);   // plane z+2 has landed
+        const int o0 = (c & 7) * T::SLOT, o1 = ((c + 1) & 7) * T::SLOT, o2 = ((c + 2) & 7) * T::SLOT,
+                  o3 = ((c + 3) & 7) * T::SLOT, o4 = ((c + 4) & 7) * T::SLOT;
+        // ---- phase A: second differences, the diagonal-sum test, survivors appended to the warp's queue ----
+        if (z < 2 || z > l - 3) phase_a_general(z, o0, o1, o2, o3, o4);
         else switch (rot) {
-            case 0: phase_a(IntC<0>()); break;
-            case 1: phase_a(IntC<1>()); break;
-            case 2: phase_a(IntC<2>()); break;
-            case 3: phase_a(IntC<3>()); break;
-            default: phase_a(IntC<4>()); break;
+            case 0: phase_a(IntC<0>(), ring + o0, ring + o1, ring + o2, ring + o3, ring + o4); break;
+            case 1: phase_a(IntC<1>(), ring + o0, ring + o1, ring + o2, ring + o3, ring + o4); break;
+            case 2: phase_a(IntC<2>(), ring + o0, ring + o1, ring + o2, ring + o3, ring + o4); break;
+            case 3: phase_a(IntC<3>(), ring + o0, ring + o1, ring + o2, ring + o3, ring + o4); break;
+            default: phase_a(IntC<4>(), ring + o0, ring + o1, ring + o2, ring + o3, ring + o4); break;
         }
         rot = rot == 4 ? 0 : rot + 1;
-        pos0 += 1 << 10;
-        tr.rotate();
-        __syncthreads();                          // appended entries and the tail are visible
-        // ---- phase B: full batches from the head of the queue (everything after the last plane) ----
-        const unsigned tail = *reinterpret_cast<volatile unsigned*>(s_tail);
-        const bool flush = z + 1 == ze;
-        while (tail - head >= (unsigned)Q::BATCH || (flush && tail != head)) {
-            const int take = (int)min(tail - head, (unsigned)Q::BATCH);
-            drain(head, take);
-            head += take;
-        }
+        off0 += plane_vox;
+        // consumer release of the oldest plane of the window (sequence number c): the arrive has release semantics, so
+        // this lane's loads of the slot are performed before the arrival is observed by the lane that refills it
+        mbar_arrive(empty_s + 8 * (c & 7));
+        // ---- phase B: full batches of this warp's queue ----
+        while (tail - head >= (unsigned)Q::BATCH) drain(Q::BATCH);
     }
+    if (tail != head) drain((int)(tail - head));  // the rest of the chunk (fewer than 64 entries)
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
     if (tx == 0 && vmax > 0.0f) atomicMax(p.minmax + 1, __float_as_int(vmax));
@@ -1977,6 +1977,12 @@ j_to_j8_kernel(const float* __restrict__ J, uint8_t* __restrict__ J8, long long 
     }
     for (long long i = 16 * n16 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         J8[i] = (uint8_t)j8_code(J[i], lo, range, y, fast, flat);
+}
+
+// Jmin = FLT_MAX, Jmax = -FLT_MAX as bit patterns (frangi.cpp:176-177) at the start of a run
+__global__ void minmax_init_kernel(int* __restrict__ minmax)
+{
+    if (threadIdx.x == 0) { minmax[0] = 0x7f7fffff; minmax[1] = (int)0xff7fffffu; }
 }
 
 // min / max over the per-slab pairs gathered on one device (local-copy multi-slab mode)

@@ -10,6 +10,9 @@
 #include <dlfcn.h>
 #include <stddef.h>
 
+#include <functional>
+#include <mutex>
+
 namespace ncclx {
 
 typedef struct ncclComm* ncclComm_t;
@@ -35,18 +38,14 @@ struct Api {
     bool ok = false;
 };
 
-inline Api& api()
+inline void load(Api& a)
 {
-    static Api a;
-    static bool tried = false;
-    if (tried) return a;
-    tried = true;
     const char* names[] = { "libnccl.so.2", "libnccl.so" };
     for (const char* n : names) {
         a.so = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (a.so) break;
     }
-    if (!a.so) return a;
+    if (!a.so) return;
 #define NCCLX_SYM(field, sym) *(void**)(&a.field) = dlsym(a.so, sym)
     NCCLX_SYM(GetUniqueId, "ncclGetUniqueId");
     NCCLX_SYM(CommInitRank, "ncclCommInitRank");
@@ -61,6 +60,14 @@ inline Api& api()
 #undef NCCLX_SYM
     a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.GroupStart &&
            a.GroupEnd && a.Send && a.Recv && a.AllReduce;
+}
+
+// handles may be created from several threads: the table is filled exactly once
+inline Api& api()
+{
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, load, std::ref(a));
     return a;
 }
 

@@ -85,6 +85,8 @@ SYMBOLS = {
     "frangi_gpu_launch_count": (C.c_uint64, []),
     "frangi_gpu_last_timings": (C.c_int, [_VP, _f32p, C.c_int]),
     "frangi_gpu_timing_depth": (C.c_int, [_VP, C.c_int]),
+    "frangi_gpu_slab_count": (C.c_int, [_VP]),
+    "frangi_gpu_warnings": (C.c_char_p, [_VP]),
     "frangi_gpu_stream": (_VP, [_VP, C.c_int]),
     "frangi_gpu_last_error": (C.c_char_p, []),
     "frangi_gpu_version": (C.c_char_p, []),

@@ -218,3 +218,33 @@ def test_overlapped_schedule_is_bit_identical():
     assert a["Jmax"] == b["Jmax"] and a["Jmin"] == b["Jmin"]
     for k in ("J", "Vx", "Vy", "Vz", "J8"):
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_back_to_back_asynchronous_runs_do_not_share_jmin_jmax():
+    """frangi_gpu_run_device with Jmin = Jmax = NULL does not synchronise.  Two different volumes launched back to
+    back must each start from Jmin = FLT_MAX, Jmax = -FLT_MAX (frangi.cpp:176-177): the pair is initialised on the
+    device, so the first run's result copy can never feed the second run's start value.  The second volume is a
+    dimmed copy of the first (smaller Jmax): a leaked Jmax would change every J8 code."""
+    import torch
+    w, h, l = 160, 128, 40
+    A = make_volume(w, h, l, seed=11, n_neurites=6)
+    B = (make_volume(w, h, l, seed=12, n_neurites=6) // 3).astype(np.uint8)
+    p = pnr_b200.FrangiPlan(SIGS, 2.0, .5, .5, 500., False, w, h, l)
+    want = {}
+    for name, I in (("A", A), ("B", B)):
+        p.upload(I)
+        lo, hi = p.run_resident()
+        want[name] = dict(p.download(want_J8=True), Jmin=lo, Jmax=hi)
+    assert want["B"]["Jmax"] < 0.5 * want["A"]["Jmax"]
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    torch.cuda.synchronize()
+    for _ in range(5):                       # no host synchronisation between the two runs
+        p.run_device(dA.data_ptr(), sync=False)
+        p.run_device(dB.data_ptr(), sync=False)
+    p.sync()
+    got = p.download(want_J8=True)
+    for k in ("J", "J8", "Vx", "Vy", "Vz"):
+        assert np.array_equal(got[k], want["B"][k]), k
+    lo, hi = p.run_device(dA.data_ptr())     # and the synchronous form after the asynchronous ones
+    assert (lo, hi) == (want["A"]["Jmin"], want["A"]["Jmax"])
+    p.close()
