@@ -566,6 +566,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)      // non-blocking: has the phase completed?
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -1308,7 +1317,12 @@ struct HessTileC {                               // 120 x 8 voxels: one row per 
 #ifndef K3C_AHEAD
 #define K3C_AHEAD 6
 #endif
+#ifndef K3C_ROT5
+#define K3C_ROT5 0                               // 1: the register rings rotate by renaming (five instantiations of phase A: no moves, but
+                                                 // 5x the code -- measured 0.4 ms per step SLOWER, instruction-cache misses); 0: by 24 moves
+#endif
     static constexpr int AHEAD = K3C_AHEAD;      // plane sequence number n is issued at iteration >= n - AHEAD (n = z + 2 at AHEAD 4)
+    static_assert(AHEAD >= 4 && AHEAD <= 7, "a warp has always released sequence number c-1 at iteration c, never c: AHEAD 8 would wait for itself");
 };
 struct HessQueue {                               // per warp
     static constexpr int BATCH = 64;             // one packed pair per lane
@@ -1317,7 +1331,7 @@ struct HessQueue {                               // per warp
     static constexpr int FIELDS = 7;
     static constexpr int WARP_FLOATS = FIELDS * CAP;
     static constexpr int BYTES = (HessTileC::NT / 32) * WARP_FLOATS * 4;
-    static constexpr int SMEM_BYTES = HessTileC::RING_BYTES + BYTES + 2 * HessTileC::SLOTS * 8;   // + full and empty mbarriers
+    static constexpr int SMEM_BYTES = HessTileC::RING_BYTES + BYTES + 2 * HessTileC::SLOTS * 8 + 16;   // + full and empty mbarriers, issue counter
 };
 
 template <int N> struct IntC { static constexpr int value = N; };
@@ -1366,6 +1380,7 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     float* qw = ring + T::SLOTS * T::SLOT + wid * Q::WARP_FLOATS;          // this warp's queue
     const uint32_t full_s = smem_u32(ring + T::SLOTS * T::SLOT + (T::NT / 32) * Q::WARP_FLOATS);
     const uint32_t empty_s = full_s + 8 * T::SLOTS;
+    int* s_next = reinterpret_cast<int*>(ring + T::SLOTS * T::SLOT + (T::NT / 32) * Q::WARP_FLOATS) + 4 * T::SLOTS;   // after the barriers
     const uint32_t ring_s = smem_u32(ring);
     int bid = blockIdx.x;
     const int bx = bid % p.ntx; bid /= p.ntx;
@@ -1385,19 +1400,25 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         mbar_init_fence();
     }
     __syncthreads();
-    // lane 0 of warp s: start the copy of plane sequence number n (n % 8 == s) into slot s
+    // start the copy of plane sequence number n into slot n % 8 (one lane)
     auto issue = [&](int n) {
         const int plane = zs - 2 + n;
-        const uint32_t bar = full_s + 8 * wid;
+        const uint32_t bar = full_s + 8 * (n & 7);
         if (plane < 0 || plane > l - 1) mbar_arrive(bar);          // beyond a z face: never read, but the phase completes
         else {
             mbar_expect_tx(bar, T::PLANE * 4);
-            tma_load_3d(ring_s + wid * (T::SLOT * 4), &p.tmap, bar, x0, y0, plane - p.f.base);
+            tma_load_3d(ring_s + (n & 7) * (T::SLOT * 4), &p.tmap, bar, x0, y0, plane - p.f.base);
         }
     };
-    int next_n = wid;                             // lane 0: the next sequence number this warp issues
-    if (tx == 0 && next_n < nseq) { issue(next_n); next_n += T::SLOTS; }
-
+    // Planes are issued in order by WHICHEVER warp first finds the next one due (within AHEAD of its own window) and
+    // its slot released by every warp: s_next is the next sequence number to issue, claimed with a compare-and-swap.
+    // No warp owns a slot, so a warp that is busy in its eigen stage never holds up the others' data.
+    if (tid == 0) {
+        const int first = min(T::SLOTS, nseq);
+        for (int n = 0; n < first; ++n) issue(n);
+        *s_next = first;
+    }
+    __syncthreads();
     const int xq = x0 + 4 * tx;                   // first voxel of the lane's quad (lanes 0 and 31: halo only)
     const int yrow = by * T::TY + wid;            // the warp's row
     const bool row_ok = yrow >= 2 && yrow <= h - 3 && tx >= 1 && tx <= 30;
@@ -1575,12 +1596,13 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
 #pragma unroll 1
     for (int c = 0; c < nz; ++c) {                // centre plane z = zs + c; its window = sequence numbers c .. c+4
         const int z = zs + c;
-        // issue duty: this warp's next plane once it is within AHEAD of the window and every warp has released the slot
+        // issue duty (see s_next above)
         if (tx == 0) {
-            while (next_n < nseq && next_n <= c + T::AHEAD) {
-                mbar_wait(empty_s + 8 * wid, (unsigned)((next_n >> 3) - 1) & 1u);
-                issue(next_n);
-                next_n += T::SLOTS;
+            for (;;) {
+                const int n = *reinterpret_cast<volatile int*>(s_next);
+                if (n >= nseq || n > c + T::AHEAD) break;
+                if (!mbar_test(empty_s + 8 * (n & 7), (unsigned)((n >> 3) - 1) & 1u)) break;   // its slot is still in use
+                if (atomicCAS(s_next, n, n + 1) == n) issue(n);
             }
         }
         __syncwarp();
@@ -1593,6 +1615,7 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
                   o3 = ((c + 3) & 7) * T::SLOT, o4 = ((c + 4) & 7) * T::SLOT;
         // ---- phase A: second differences, the diagonal-sum test, survivors appended to the warp's queue ----
         if (z < 2 || z > l - 3) phase_a_general(z, o0, o1, o2, o3, o4);
+#if K3C_ROT5
         else switch (rot) {
             case 0: phase_a(IntC<0>(), ring + o0, ring + o1, ring + o2, ring + o3, ring + o4); break;
             case 1: phase_a(IntC<1>(), ring + o0, ring + o1, ring + o2, ring + o3, ring + o4); break;
@@ -1601,6 +1624,17 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
             default: phase_a(IntC<4>(), ring + o0, ring + o1, ring + o2, ring + o3, ring + o4); break;
         }
         rot = rot == 4 ? 0 : rot + 1;
+#else
+        else {                                    // one instantiation, the rings shifted by register moves (24 per plane)
+            phase_a(IntC<0>(), ring + o0, ring + o1, ring + o2, ring + o3, ring + o4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                C[0][k] = C[1][k]; C[1][k] = C[2][k]; C[2][k] = C[3][k]; C[3][k] = C[4][k];
+                G[1][k] = G[2][k]; G[2][k] = G[3][k];
+            }
+        }
+        (void)rot;
+#endif
         off0 += plane_vox;
         // consumer release of the oldest plane of the window (sequence number c): the arrive has release semantics, so
         // this lane's loads of the slot are performed before the arrival is observed by the lane that refills it
