@@ -24,9 +24,11 @@ Our arm prints ONE JSON line with
 
 The reference arm times oracle/_ref/libpnr_ref.so (the reference's own frangi.cpp,
 compiled unmodified; falls back to the C port in oracle/ when that file did not
-travel) on all host cores, each step a bounded sample: one 256x256x64 sub-block
-of the workload per core, every core running the reference's single-threaded
-frangi3d on its own block concurrently.
+travel) on all host cores, each step a bounded sample: one block of FULL-WIDTH rows
+of the workload per core (w x 64 x 32 voxels: the x stride of the real planes, which
+is what the reference's stride-w y pass sees; a z stride of 512 KB, which like the
+real 16 MB maps every tap of the stride-w*h z pass to one cache set), every core
+running the reference's single-threaded frangi3d on its own block concurrently.
 
 Nothing here reads /root/reference.  oracle/ is executed only in the
 cpu_baseline leg and in the reference arm, never on the measured product path.
@@ -52,7 +54,20 @@ METRIC = "frangi_3scale_voxels_per_s"
 UNIT = "voxel/s"
 ZDIST, ALPHA, BETA, CC = 2.0, 0.5, 0.5, 500.0
 BASE_BLOCK = (512, 512, 128)      # seeded synthetic block (w, h, l) that is tiled to the workload
-CPU_BLOCK = (256, 256, 64)        # per-core sample of the CPU arms (BASELINE.json configs[0] shape)
+CPU_BLOCK_HL = (64, 32)           # per-core sample of the CPU arms: full-width rows of the workload, 64 rows, 32 planes
+
+
+def cpu_block(w):
+    return (w, CPU_BLOCK_HL[0], CPU_BLOCK_HL[1])
+
+
+def config_name(w, h, l, sigmas):
+    """Which BASELINE.json config a workload is (the label printed in config.workload)."""
+    sig = [float(x) for x in sigmas]
+    table = {((256, 256, 64), (2.0, 4.0, 6.0)): "configs[0]", ((512, 512, 128), (2.0, 4.0, 6.0)): "configs[1]",
+             ((1024, 1024, 256), (1.0, 2.0, 3.0, 4.0, 5.0, 6.0)): "configs[2]",
+             ((2048, 2048, 512), (2.0, 4.0, 6.0)): "configs[3], the volume the metric's target is quoted on"}
+    return table.get(((w, h, l), tuple(sig)), "not a BASELINE.json config")
 
 # SURVEY.md section 8(d): algorithmic work per voxel
 def pipeline_bytes_per_voxel(S):          # 16 + 17 (S - 1)
@@ -93,8 +108,11 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--pageable", action="store_true",
                     help="e2e with ordinary (pageable) host buffers, as an unmodified caller would pass them")
-    ap.add_argument("--verify", action="store_true",
-                    help="N > 1: check every rank's slab of J / V bit for bit against a one-GPU run of the whole volume on rank 0")
+    ap.add_argument("--no-verify", action="store_true",
+                    help="N > 1: skip the check of every rank's slab of J / V, bit for bit, against an independent one-GPU "
+                         "run of the same planes (on by default)")
+    ap.add_argument("--no-exact", action="store_true", help="skip the extra timing of the bit-exact smoothing mode")
+    ap.add_argument("--outputs", default="", help="extra outputs kept by the handle: comma list of dir, scale")
     return ap.parse_args()
 
 
@@ -174,13 +192,14 @@ _WORKER_CACHE = {}
 
 
 def _cpu_worker(args):
-    """One core: the reference's single-threaded frangi3d on its own 256x256x64 block."""
-    kind, block_index, sigmas = args
+    """One core: the reference's single-threaded frangi3d on its own block of full-width rows."""
+    kind, block_index, sigmas, wblk = args
     from oracle import Oracle, Reference
     from pnr_b200.synth import make_volume
-    w, h, l = CPU_BLOCK
+    w, h, l = cpu_block(wblk)
     if "I" not in _WORKER_CACHE:          # each worker process keeps its block and its library
-        _WORKER_CACHE["I"] = make_volume(w, h, l, seed=20181009 + os.getpid() % 1000)
+        base = make_volume(min(w, BASE_BLOCK[0]), h, l, seed=20181009 + os.getpid() % 1000)
+        _WORKER_CACHE["I"] = np.ascontiguousarray(np.tile(base, (1, 1, -(-w // base.shape[2])))[:, :, :w])
         _WORKER_CACHE["impl"] = Reference() if kind == "reference" else Oracle()
     I, impl = _WORKER_CACHE["I"], _WORKER_CACHE["impl"]
     t0 = time.perf_counter()
@@ -206,20 +225,23 @@ def cpu_cores():
 class CpuArm:
     """P worker processes, one per host core; one step = every worker runs one block."""
 
-    def __init__(self, sigmas):
+    def __init__(self, sigmas, w):
         import multiprocessing as mp
+        from oracle import Oracle, Reference
         self.kind = cpu_kind()
-        if self.kind == "port":
-            from oracle import Oracle
-            Oracle()                      # builds liboracle.so once, before the workers fork
+        # the library is loaded in the parent BEFORE the workers fork, so that it shows in this process's map
+        # (the driver's native_so_loaded) and every worker inherits it
+        self.impl = Reference() if self.kind == "reference" else Oracle()
         self.cores = cpu_cores()
         self.sigmas = list(sigmas)
+        self.w = w
+        self.block = cpu_block(w)
         self.pool = mp.get_context("fork").Pool(self.cores)
-        self.voxels_per_step = self.cores * CPU_BLOCK[0] * CPU_BLOCK[1] * CPU_BLOCK[2]
+        self.voxels_per_step = self.cores * self.block[0] * self.block[1] * self.block[2]
 
     def step(self):
         t0 = time.perf_counter()
-        self.pool.map(_cpu_worker, [(self.kind, i, self.sigmas) for i in range(self.cores)], chunksize=1)
+        self.pool.map(_cpu_worker, [(self.kind, i, self.sigmas, self.w) for i in range(self.cores)], chunksize=1)
         return time.perf_counter() - t0
 
     def close(self):
@@ -227,16 +249,17 @@ class CpuArm:
         self.pool.join()
 
     def sample_text(self):
+        b = self.block
         return (f"{self.cores} concurrent single-threaded frangi3d calls, one per host core, each on its own "
-                f"{CPU_BLOCK[0]}x{CPU_BLOCK[1]}x{CPU_BLOCK[2]} seeded block of the workload per step "
-                f"(wall clock around the whole step)")
+                f"{b[0]}x{b[1]}x{b[2]} block of full-width rows of the workload per step (the real x stride; "
+                f"wall clock around the whole step)")
 
 
 def run_reference_arm(a, sigmas, w, h, l):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    arm = CpuArm(sigmas)
+    arm = CpuArm(sigmas, w)
     for _ in range(a.warmup):
         arm.step()
     t = [arm.step() for _ in range(a.steps)]
@@ -247,7 +270,8 @@ def run_reference_arm(a, sigmas, w, h, l):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"frangi3d sigma={a.sigmas} zdist=2 on {w}x{h}x{l} uint8 (BASELINE.json configs[3])",
+        "config": {"workload": f"frangi3d sigma={a.sigmas} zdist=2 alpha=beta=0.5 C=500 on {w}x{h}x{l} uint8 "
+                               f"(BASELINE.json {config_name(w, h, l, sigmas)})",
                    "sample": arm.sample_text()},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
                          "sample": arm.sample_text()},
@@ -284,6 +308,11 @@ def run_ours(a, sigmas, w, h, l):
 
     lib = pnr_b200.load_library()
     flags = 0 if a.exact else pnr_b200.FLAG_FMA_SMOOTHING
+    extra = [x for x in a.outputs.split(",") if x]
+    if "dir" in extra:
+        flags |= pnr_b200.FLAG_DIR_F32
+    if "scale" in extra:
+        flags |= pnr_b200.FLAG_SCALE_IDX
     z0, z1 = l * rank // world, l * (rank + 1) // world
     nz = z1 - z0
     own_vox = w * h * nz
@@ -346,34 +375,70 @@ def run_ours(a, sigmas, w, h, l):
     ms_per_step = ms_total / a.steps
     value = total_vox / (ms_per_step * 1e-3)
 
-    # ---- optional: N-slab result == 1-GPU result, bit for bit --------------------------
+    # ---- N-slab result == independent one-GPU result, bit for bit (every run with N > 1) -------------------------
+    # Every rank recomputes ITS planes with a second, single-slab handle over the sub-volume [z0 - H, z1 + H) clipped
+    # to the volume, H = ceil(3 sigma_max / zdist) + 2: every stage is z-local with that radius and the clamp /
+    # one-sided rules of the sub-volume's ends only touch planes within H of them, so the planes [z0, z1) of the
+    # sub-volume run are exactly what a whole-volume run produces there.  No exchange, no NCCL in the
+    # checker: it shares nothing with the slab path but the kernels.  Jmin / Jmax (global scalars) are compared
+    # through the all-gathered maxima.
     verify = None
-    if a.verify:
+    if world > 1 and not a.no_verify:
+        import math
         import zlib
-        out = plan.download()
-        crc = [zlib.crc32(out[k].tobytes()) for k in ("J", "Vx", "Vy", "Vz")]
-        mine = torch.tensor(crc + [z0, z1], dtype=torch.int64, device=dev)
-        allr = [torch.zeros_like(mine) for _ in range(world)]
+        H = max(math.ceil(3 * (sg / ZDIST)) for sg in sigmas) + 2
+        za, zb = max(z0 - H, 0), min(z1 + H, l)
+        out = plan.download(want_J8=False)
+        sub = FrangiPlan(sigmas, ZDIST, ALPHA, BETA, CC, False, w, h, zb - za, flags=flags, devices=(local_rank,))
+        sub.upload(workload_slab(w, h, l, za, zb))
+        sub_lo, sub_hi = sub.run_resident()
+        ref = sub.download(want_J8=False)
+        sub.close()
+        keys = [k for k in ("J", "Vx", "Vy", "Vz", "scale", "dir") if out.get(k) is not None]
+        bad_keys = []
+        for k in keys:
+            got = out[k]
+            want = ref[k][:, z0 - za:z1 - za] if k == "dir" else ref[k][z0 - za:z1 - za]
+            if not np.array_equal(got, want):
+                bad_keys.append(k)
+        own_max = float(ref["J"][z0 - za:z1 - za].max())
+        flag = torch.tensor([1 if bad_keys else 0, zlib.crc32(out["J"].tobytes())], dtype=torch.int64, device=dev)
+        mx = torch.tensor([own_max], dtype=torch.float64, device=dev)
+        allf = [torch.zeros_like(flag) for _ in range(world)]
+        dist.all_gather(allf, flag)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        verify = {"method": "every rank's planes recomputed by an independent single-slab handle over its sub-volume "
+                            f"[z0-{H}, z1+{H}); J, V (and scale / dir when kept) compared bit for bit",
+                  "slabs": world, "mismatching_ranks": [r_ for r_, t_ in enumerate(allf) if int(t_[0].item())],
+                  "slab_crc32_J": [int(t_[1].item()) for t_ in allf],
+                  "jmax_slabs": jmax, "jmax_independent": float(mx.item())}
+        if float(mx.item()) != jmax and 0 not in verify["mismatching_ranks"]:
+            verify["mismatching_ranks"].append(-1)         # the global maximum disagrees
+        del out, ref
+
+    # ---- the bit-exact smoothing mode (separately rounded multiply and add), timed beside the FMA mode -----------
+    exact_ms = None
+    if world == 1 and not a.exact and not a.no_exact:
+        pe = FrangiPlan(sigmas, ZDIST, ALPHA, BETA, CC, False, w, h, l, flags=flags & ~pnr_b200.FLAG_FMA_SMOOTHING,
+                        devices=(local_rank,))
+        pe.upload(hI.array)
+        for _ in range(3):
+            pe.run_resident(sync=False)
+        pe.sync()
+        se = torch.cuda.ExternalStream(pe.stream(0), device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(se)
+        for _ in range(a.steps):
+            pe.run_resident(sync=False)
+        e1.record(se)
+        pe.sync()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_gather(allr, mine)
-        else:
-            allr = [mine]
-        if rank == 0:
-            whole = FrangiPlan(sigmas, ZDIST, ALPHA, BETA, CC, False, w, h, l, flags=flags, devices=(local_rank,))
-            hw = workload_slab(w, h, l, 0, l)
-            whole.upload(hw)
-            wj = whole.run_resident()
-            ref = whole.download()
-            whole.close()
-            bad = []
-            for r_, t_ in enumerate(allr):
-                t_ = [int(x) for x in t_.cpu()]
-                a0, a1 = t_[4], t_[5]
-                want = [zlib.crc32(ref[k][a0:a1].tobytes()) for k in ("J", "Vx", "Vy", "Vz")]
-                if want != t_[:4]:
-                    bad.append(r_)
-            verify = {"slabs": world, "mismatching_ranks": bad, "jmax_whole": wj[1], "jmax_slabs": jmax}
-        del out
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        exact_ms = float(te.item()) / a.steps
+        pe.close()
 
     # ---- end to end through the C-ABI call with host buffers ----------------------
     e2e = None
@@ -424,6 +489,21 @@ def run_ours(a, sigmas, w, h, l):
                                  "d2h_bytes_per_step": int(total_vox * 4 + 8),
                                  "call": "frangi_gpu_run(I_host -> J8, Vx, Vy, Vz host u8; J_host = NULL)"}
             hJ8.free()
+        # the buffers as the unmodified call site passes them (new float[size], Advantra_plugin.cpp:2490-2494): pageable
+        if world == 1 and not a.pageable:
+            pJ = np.zeros((nz, h, w), np.float32)
+            pV = [np.zeros((nz, h, w), np.uint8) for _ in range(3)]
+            pI = np.array(hI.array)
+            plan.run(pI, J=pJ, Vx=pV[0], Vy=pV[1], Vz=pV[2])
+            t0 = time.perf_counter()
+            kp = min(k_e2e, 2)
+            for _ in range(kp):
+                plan.run(pI, J=pJ, Vx=pV[0], Vy=pV[1], Vz=pV[2])
+            torch.cuda.synchronize()
+            dtp = time.perf_counter() - t0
+            e2e["pageable"] = {"value": total_vox * kp / dtp, "unit": UNIT, "ms_per_step": 1e3 * dtp / kp, "steps": kp,
+                               "call": "the same call with ordinary (pageable) host buffers"}
+            del pJ, pV, pI
         for b in [hJ] + hV:
             b.free()
 
@@ -492,7 +572,7 @@ def run_ours(a, sigmas, w, h, l):
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         try:
-            arm = CpuArm(sigmas)
+            arm = CpuArm(sigmas, w)
             t = [arm.step() for _ in range(2)]
             arm.close()
             cpu = {"value": arm.voxels_per_step / min(t), "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
@@ -506,7 +586,7 @@ def run_ours(a, sigmas, w, h, l):
         "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": f"frangi3d sigma={a.sigmas} zdist=2 alpha=beta=0.5 C=500 on {w}x{h}x{l} uint8 "
-                        f"(BASELINE.json configs[3]), z-slabs over {world} GPU(s)",
+                        f"(BASELINE.json {config_name(w, h, l, sigmas)}), z-slabs over {world} GPU(s)",
             "input": f"seeded {BASE_BLOCK[0]}x{BASE_BLOCK[1]}x{BASE_BLOCK[2]} synthetic neuron block tiled to the volume",
             "smoothing": "exact (rounded mul+add, bit-identical to the reference)" if a.exact
                          else "fma (within BASELINE tolerance; --exact for the bit-identical mode)",
@@ -516,6 +596,8 @@ def run_ours(a, sigmas, w, h, l):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "jmin": jmin, "jmax": jmax,
     }
+    if exact_ms is not None:
+        line["exact_ms_per_step"] = exact_ms
     if seed_prepass is not None:
         line["seed_prepass"] = seed_prepass
     if verify is not None:

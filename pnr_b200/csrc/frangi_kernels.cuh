@@ -649,7 +649,7 @@ struct TileRing {
 #endif
 struct ZTile {
     static constexpr int COLS = 128, DEPTH = ZT_DEPTH, WARPS = ZT_WARPS;   // a lane owns 4 adjacent columns
-    static constexpr int SMEM_BYTES = WARPS * DEPTH * (COLS * 4 + 16);          // rings, one full and one empty mbarrier per slot
+    static constexpr int SMEM_BYTES = WARPS * (DEPTH * (COLS * 4 + 16) + 128);  // rings, one full and one empty mbarrier per slot, one scratch word per lane
 };
 
 template <int LZ, bool EXACT>
@@ -675,6 +675,7 @@ gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     const uint32_t bar_s = smem_u32(zring + ZTile::WARPS * D * ZTile::COLS) + warp * D * 8;
     // one "empty" mbarrier per slot next to the "full" one: the consumer-release half of the producer / consumer pair
     const uint32_t empty_s = smem_u32(zring + ZTile::WARPS * D * ZTile::COLS) + ZTile::WARPS * D * 8 + warp * D * 8;
+    const uint32_t scratch_s = smem_u32(zring + ZTile::WARPS * D * ZTile::COLS) + 2 * ZTile::WARPS * D * 8 + warp * 128 + lane * 4;
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < D; ++k) { mbar_init(bar_s + 8 * k, 1); mbar_init(empty_s + 8 * k, 32); }
@@ -699,12 +700,16 @@ gauss_z_tma_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     auto next = [&](int j) {                                   // input j of the chunk, this lane's four columns
         mbar_wait(bar_s + 8 * slot, par);
         const float4 v = *reinterpret_cast<const float4*>(ring + slot * ZTile::COLS + 4 * lane);
-        // Slot reuse is ordered by the standard full / empty barrier pair: every lane ARRIVES on the slot's empty
-        // barrier after its load (the arrive has release semantics: the load is performed before the arrival is
-        // observed) and lane 0 WAITS for all 32 arrivals before it arms the full barrier and issues the refill.
-        // A refill that is merely issued after the load INSTRUCTION can land, served from L2, while a quarter-warp
-        // of the load is still queued in the memory pipeline -- seen as rare 16-byte corruptions when NCCL kernels
-        // ran beside this one (round 1; then closed with a dependent dummy store, now with the documented pattern).
+        // Slot reuse is ordered by a full / empty barrier pair: every lane ARRIVES on the slot's empty barrier once its
+        // load has DELIVERED and lane 0 WAITS for all 32 arrivals before it arms the full barrier and issues the refill.
+        // "Delivered" needs care: the value is first used many instructions later, and neither program order nor the
+        // release semantics of the arrive make the hardware hold the arrive back until the load's data has returned
+        // (measured twice: a refill issued right after the load INSTRUCTION -- by plain program order in round 1, behind
+        // an arrive that directly follows the load in round 2 -- lands, served from L2, while a quarter-warp of the load
+        // is still queued in the memory pipeline: rare 16-byte corruptions, tools/debug_streamed.py).  So the arrive is
+        // made data-dependent on the load: a store of the loaded value cannot issue before the data is in the
+        // register, and the arrive follows it in the same in-order memory pipe.
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch_s), "f"(v.w) : "memory");
         mbar_arrive(empty_s + 8 * slot);
         if (lane == 0 && j + D < nin) {
             mbar_wait(empty_s + 8 * slot, par);                // use k of the slot completes phase k of both barriers
