@@ -30,6 +30,7 @@
 #include "frangi2d_kernels.cuh"
 #include "soma_kernels.cuh"
 #include "nccl_dyn.h"
+#include "host_stager.h"
 
 #define FRANGI_API extern "C" __attribute__((visibility("default")))
 
@@ -265,6 +266,9 @@ struct Slab {
     // overlapped schedule (one-slab handles, run_pipeline): a second Fxy / F buffer pair with its descriptors, the
     // low-priority stream of the z pass, and per-kernel timing events (6 per scale and timing set)
     float *dFxyB = nullptr, *dFB = nullptr;
+    float* dFxyA = nullptr;        // the first Fxy buffer (dFxy points at the one of the scale in hand)
+    CUtensorMap tmFxyA{};
+    cudaEvent_t ev_halo2 = nullptr; // halo events alternate with the Fxy buffers (ev_halo: even scales)
     CUtensorMap tmFB{}, tmFcB{}, tmFxyB{};
     cudaStream_t s_aux = nullptr;
     std::vector<cudaEvent_t> ev_ov;
@@ -298,6 +302,7 @@ struct frangi_gpu {
     bool ran = false;
     bool local_halo = false;     // halos move by peer copies inside this process instead of NCCL
     int stream_chunk = -1;       // frangi_gpu_run: planes per pipelined chunk; 0 = off, -1 = automatic
+    HostStager stager;           // pinned slots + host threads for calls with pageable host buffers (frangi_gpu_run)
     bool last_streamed = false;  // the last run recorded no per-class events
     bool overlap = false;        // one-slab handle on the overlapped schedule (see run_pipeline)
     int timing_depth = 1;        // event sets kept per slab
@@ -311,7 +316,7 @@ void free_slab(Slab& s)
 {
     cudaSetDevice(s.dev);
     if (s.comm && ncclx::api().ok) ncclx::api().CommDestroy(s.comm);
-    cudaFree(s.dI); cudaFree(s.dFxy); cudaFree(s.dF); cudaFree(s.dJ);
+    cudaFree(s.dI); cudaFree(s.dFxyA ? s.dFxyA : s.dFxy); cudaFree(s.dF); cudaFree(s.dJ);
     cudaFree(s.dVx); cudaFree(s.dVy); cudaFree(s.dVz); cudaFree(s.dScale); cudaFree(s.dJ8);
     cudaFree(s.dDir); cudaFree(s.dMinMax);
     s.seed.release();
@@ -319,6 +324,7 @@ void free_slab(Slab& s)
     for (auto e : s.ev_all) cudaEventDestroy(e);
     if (s.ev_boundary) cudaEventDestroy(s.ev_boundary);
     if (s.ev_halo) cudaEventDestroy(s.ev_halo);
+    if (s.ev_halo2) cudaEventDestroy(s.ev_halo2);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     cudaFree(s.dGather);
     cudaFree(s.dFxyB); cudaFree(s.dFB);
@@ -435,6 +441,15 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     // finite from the start: a z pass whose template radius exceeds the true one reads a few planes with zero taps,
     // possibly halo planes that have not arrived yet (0 x finite = 0; never 0 x garbage)
     CK(cudaMemset(s.dFxy, 0, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
+    s.dFxyA = s.dFxy; s.tmFxyA = s.tmFxy;
+    if (H->nslabs_total > 1 && H->scales.size() > 1) {
+        // multi-slab: two Fxy buffers alternate by scale, so that the xy pass and the halo exchange of scale s+1 (s+2)
+        // are issued before the z pass of scale s has read its own buffer (run_pipeline)
+        CK(cudaMalloc(&s.dFxyB, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
+        CK(cudaMemset(s.dFxyB, 0, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
+        RC(make_tile_map(&s.tmFxyB, s.dFxyB, H->w, H->h, s.xe - s.xb, H->fpitch, H->fplane, ZTile::COLS, 1));
+        CK(cudaEventCreateWithFlags(&s.ev_halo2, cudaEventDisableTiming));
+    }
     if (H->overlap) {
         CK(cudaMalloc(&s.dFxyB, sizeof(float) * (size_t)H->fplane * (s.xe - s.xb)));
         CK(cudaMalloc(&s.dFB, sizeof(float) * (size_t)H->fplane * (s.fe - s.fb)));
@@ -464,12 +479,13 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
 
 // xy smoothing (K1) of nz dense planes I -> out
 int launch_xy_planes(const uint8_t* I, float* out, int w, int h, int nz, int fpitch, long long fplane, const ScalePlan& sp,
-                     unsigned flags, cudaStream_t st)
+                     unsigned flags, cudaStream_t st, int zsplit = -1, int zgap = 0)
 {
     if (nz <= 0) return 0;
     XYParams p;
     p.I = I; p.out = out;
     p.w = w; p.h = h; p.nz = nz;
+    p.zsplit = zsplit < 0 ? nz : zsplit; p.zgap = zgap;
     p.fpitch = fpitch; p.fplane = fplane;
     p.nstrips = (w + 255) / 256;
     // enough CTAs to fill 148 SMs a few times over, else split y into segments
@@ -493,6 +509,13 @@ int launch_xy_planes(const uint8_t* I, float* out, int w, int h, int nz, int fpi
 }
 
 // xy smoothing of own planes [z0, z1) of slab s for one scale
+// the planes [z0, z0 + n) and [z1 - n, z1) of a slab (its two boundary groups, n < (z1 - z0) / 2) in ONE launch
+int launch_xy_ends(frangi_gpu* H, Slab& s, const ScalePlan& sp, const uint8_t* I_own, int z0, int z1, int n)
+{
+    return launch_xy_planes(I_own + (long long)(z0 - s.zb) * H->w * H->h, s.dFxy + (long long)(z0 - s.xb) * H->fplane, H->w, H->h,
+                            2 * n, H->fpitch, H->fplane, sp, H->flags, s.s_main, n, (z1 - z0) - 2 * n);
+}
+
 int launch_xy(frangi_gpu* H, Slab& s, const ScalePlan& sp, const uint8_t* I_own, int z0, int z1)
 {
     if (z1 <= z0) return 0;
@@ -794,25 +817,31 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
         g_launches++;
         CK(cudaEventRecord(s.ev_time[0], s.s_main));
     }
-    // Multi-slab: the xy pass of a scale on every local slab -- boundary planes first, then the halo exchange on the
-    // comm streams, then the interior planes while the exchange is in flight.
+    // Multi-slab.  Two Fxy buffers alternate by scale (buffer si & 1, halo event si & 1), so a scale's xy pass and halo
+    // exchange never wait for an earlier scale's z pass to have read "the" Fxy buffer.
+    auto use_fxy = [&](Slab& s, int si) {
+        const bool b = (si & 1) && s.dFxyB;
+        s.dFxy = b ? s.dFxyB : s.dFxyA;
+        s.dFxy0 = s.dFxy;
+        s.tmFxy = b ? s.tmFxyB : s.tmFxyA;
+    };
+    auto halo_event = [&](Slab& s, int si) { return ((si & 1) && s.ev_halo2) ? s.ev_halo2 : s.ev_halo; };
+    // The xy pass of scale si on every local slab -- both boundary plane groups in ONE launch, then the halo
+    // exchange of those planes on the comm streams, then the interior planes while the exchange is in flight.
     auto xy_and_exchange = [&](int si) -> int {
         const ScalePlan& sp = H->scales[si];
         const int halo = sp.rz + 2;
         for (size_t k = 0; k < H->slabs.size(); ++k) {
             Slab& s = H->slabs[k];
             CK(cudaSetDevice(s.dev));
-            if (H->local_halo && si > 0) {   // neighbours have pulled the previous scale's boundary planes
-                if (k > 0) CK(cudaStreamWaitEvent(s.s_main, H->slabs[k - 1].ev_halo, 0));
-                if (k + 1 < H->slabs.size()) CK(cudaStreamWaitEvent(s.s_main, H->slabs[k + 1].ev_halo, 0));
+            use_fxy(s, si);
+            if (H->local_halo && si >= 2) {  // neighbours have pulled the boundary planes this buffer held two scales ago
+                if (k > 0) CK(cudaStreamWaitEvent(s.s_main, halo_event(H->slabs[k - 1], si), 0));
+                if (k + 1 < H->slabs.size()) CK(cudaStreamWaitEvent(s.s_main, halo_event(H->slabs[k + 1], si), 0));
             }
             const int nz = s.ze - s.zb;
-            if (nz <= 2 * halo) {
-                RC(launch_xy(H, s, sp, I_own[k], s.zb, s.ze));
-            } else {
-                RC(launch_xy(H, s, sp, I_own[k], s.zb, s.zb + halo));
-                RC(launch_xy(H, s, sp, I_own[k], s.ze - halo, s.ze));
-            }
+            if (nz <= 2 * halo) RC(launch_xy(H, s, sp, I_own[k], s.zb, s.ze));
+            else RC(launch_xy_ends(H, s, sp, I_own[k], s.zb, s.ze, halo));
             CK(cudaEventRecord(s.ev_boundary, s.s_main));
             CK(cudaStreamWaitEvent(s.s_comm, s.ev_boundary, 0));
         }
@@ -820,7 +849,7 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
         for (size_t k = 0; k < H->slabs.size(); ++k) {
             Slab& s = H->slabs[k];
             CK(cudaSetDevice(s.dev));
-            CK(cudaEventRecord(s.ev_halo, s.s_comm));
+            CK(cudaEventRecord(halo_event(s, si), s.s_comm));
             const int nz = s.ze - s.zb;
             if (nz > 2 * halo) RC(launch_xy(H, s, sp, I_own[k], s.zb + halo, s.ze - halo));
         }
@@ -829,23 +858,30 @@ int run_pipeline(frangi_gpu* H, const std::vector<const uint8_t*>& I_own)
     for (int si = 0; si < S; ++si) {
         const ScalePlan& sp = H->scales[si];
         if (multi) {
-            // Scales are software-pipelined so that a halo exchange never waits in the open: the xy pass and the
-            // exchange of scale si+1 are issued BEFORE the Hessian / eigen stage of scale si (which reads neither Fxy
-            // nor the halo), so the exchange has that whole stage to finish.  Per scale and slab: wait for the halo,
-            // ONE z pass over all F planes, [xy pass + exchange of the next scale], ONE Hessian / eigen launch -- no
-            // plane is smoothed or staged twice.  The single Fxy / F buffers are safe: the next xy pass follows this
-            // scale's z pass on the same stream, and the next z pass follows this scale's Hessian / eigen stage.
-            if (si == 0) RC(xy_and_exchange(0));
+            // Scales are software-pipelined two deep so that a halo exchange never waits in the open: the run starts
+            // with the xy passes and exchanges of scales 0 AND 1 (the first exchange hides behind the second xy pass),
+            // and the xy pass + exchange of scale si+2 are issued right after the z pass of scale si -- the last
+            // reader of that Fxy buffer -- and BEFORE its Hessian / eigen stage (which reads neither Fxy nor the
+            // halo).  Per scale and slab: wait for the halo, ONE z pass over all F planes, [xy + exchange of scale
+            // si+2], ONE Hessian / eigen launch: no plane is smoothed or staged twice.  The single F buffer is safe:
+            // the next z pass follows this scale's Hessian / eigen stage on the same stream.  A receive into a
+            // buffer's halo planes cannot start before the z pass that last read them is done: the comm stream waits
+            // for the boundary event, which follows that z pass on the main stream.
+            if (si == 0) {
+                RC(xy_and_exchange(0));
+                if (S > 1) RC(xy_and_exchange(1));
+            }
             for (auto& s : H->slabs) {
                 CK(cudaSetDevice(s.dev));
                 cudaEvent_t* ev = s.ev_time + kEvPerScale * si;
                 CK(cudaEventRecord(ev[1], s.s_main));
-                CK(cudaStreamWaitEvent(s.s_main, s.ev_halo, 0));
+                CK(cudaStreamWaitEvent(s.s_main, halo_event(s, si), 0));
                 CK(cudaEventRecord(ev[2], s.s_main));
+                use_fxy(s, si);
                 RC(launch_z(H, s, sp));
                 CK(cudaEventRecord(ev[3], s.s_main));
             }
-            if (si + 1 < S) RC(xy_and_exchange(si + 1));
+            if (si + 2 < S) RC(xy_and_exchange(si + 2));
             for (auto& s : H->slabs) {
                 CK(cudaSetDevice(s.dev));
                 cudaEvent_t* ev = s.ev_time + kEvPerScale * si;
@@ -1066,6 +1102,22 @@ int run_streamed(frangi_gpu* H, const uint8_t* I_host, float* J, uint8_t* Vx, ui
     if (sc && !s.dScale) return fail(FRANGI_GPU_ESTATE, "scale index not kept: create with FRANGI_GPU_FLAG_SCALE_IDX");
     if (dir && !s.dDir) return fail(FRANGI_GPU_ESTATE, "float direction not kept: create with FRANGI_GPU_FLAG_DIR_F32");
     CK(cudaSetDevice(s.dev));
+    // Ordinary (pageable) host buffers -- what the unmodified call site passes, Advantra_plugin.cpp:2490-2494 -- go
+    // through the pinned staging ring (host_stager.h); pinned buffers are copied directly.
+    const void* outs[] = { J, Vx, Vy, Vz, J8, sc, dir };
+    bool staged_out = false;
+    for (const void* q : outs) staged_out = staged_out || (q && H->stager.pageable(q));
+    const bool staged_in = H->stager.pageable(I_host);
+    if (staged_in || staged_out) {
+        // the host-side memcpy must keep up with the DMA (~54 GB/s on PCIe 5): one core moves 4-5 GB/s
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int nthreads = (int)std::max(2u, std::min(16u, hw > 2 ? hw - 2 : 1u));
+        if (!H->stager.start(s.dev, 24, nthreads)) return fail(FRANGI_GPU_ENOMEM, "pinned staging ring: allocation failed");
+    }
+    auto down = [&](void* dst, const void* src, size_t bytes, cudaStream_t st) -> cudaError_t {
+        if (H->stager.pageable(dst)) return H->stager.d2h(dst, src, bytes, st);
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+    };
     while ((int)s.ev_chunk.size() < 2 * nch) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1092,8 +1144,11 @@ int run_streamed(frangi_gpu* H, const uint8_t* I_host, float* J, uint8_t* Vx, ui
         const uint8_t* I_view = s.dI + off;
         const int need_hi = std::min(v.fe + H->rz_max, s.ze);
         if (need_hi > uploaded) {
-            CK(cudaMemcpyAsync(s.dI + (size_t)(uploaded - s.zb) * wh, I_host + (size_t)(uploaded - s.zb) * wh,
-                               (size_t)(need_hi - uploaded) * wh, cudaMemcpyHostToDevice, s.s_h2d));
+            uint8_t* dst = s.dI + (size_t)(uploaded - s.zb) * wh;
+            const uint8_t* src = I_host + (size_t)(uploaded - s.zb) * wh;
+            const size_t nb = (size_t)(need_hi - uploaded) * wh;
+            if (staged_in) CK(H->stager.h2d(dst, src, nb, s.s_h2d));
+            else CK(cudaMemcpyAsync(dst, src, nb, cudaMemcpyHostToDevice, s.s_h2d));
             uploaded = need_hi;
         }
         CK(cudaEventRecord(s.ev_chunk[2 * c], s.s_h2d));
@@ -1108,24 +1163,24 @@ int run_streamed(frangi_gpu* H, const uint8_t* I_host, float* J, uint8_t* Vx, ui
         CK(cudaEventRecord(s.ev_chunk[2 * c + 1], s.s_main));
         CK(cudaStreamWaitEvent(s.s_d2h, s.ev_chunk[2 * c + 1], 0));
         const size_t n = (size_t)(cz1 - cz0) * wh;
-        if (J) CK(cudaMemcpyAsync(J + off, v.dJ, n * 4, cudaMemcpyDeviceToHost, s.s_d2h));
-        if (Vx) CK(cudaMemcpyAsync(Vx + off, v.dVx, n, cudaMemcpyDeviceToHost, s.s_d2h));
-        if (Vy) CK(cudaMemcpyAsync(Vy + off, v.dVy, n, cudaMemcpyDeviceToHost, s.s_d2h));
-        if (Vz) CK(cudaMemcpyAsync(Vz + off, v.dVz, n, cudaMemcpyDeviceToHost, s.s_d2h));
-        if (sc) CK(cudaMemcpyAsync(sc + off, v.dScale, n, cudaMemcpyDeviceToHost, s.s_d2h));
+        if (J) CK(down(J + off, v.dJ, n * 4, s.s_d2h));
+        if (Vx) CK(down(Vx + off, v.dVx, n, s.s_d2h));
+        if (Vy) CK(down(Vy + off, v.dVy, n, s.s_d2h));
+        if (Vz) CK(down(Vz + off, v.dVz, n, s.s_d2h));
+        if (sc) CK(down(sc + off, v.dScale, n, s.s_d2h));
         if (dir)
             for (int k = 0; k < 3; ++k)
-                CK(cudaMemcpyAsync(dir + (size_t)k * s.voxels + off, v.dDir + (size_t)k * s.voxels, n * 4,
-                                   cudaMemcpyDeviceToHost, s.s_d2h));
+                CK(down(dir + (size_t)k * s.voxels + off, v.dDir + (size_t)k * s.voxels, n * 4, s.s_d2h));
     }
     // the 8-bit map needs the global min / max: after the last chunk
     const int nb = (int)std::min<long long>((s.voxels + 255) / 256, 148 * 16);
     j_to_j8_kernel<<<nb, 256, 0, s.s_main>>>(s.dJ, s.dJ8, s.voxels, s.dMinMax);
     g_launches++;
     CK(cudaGetLastError());
-    if (J8) CK(cudaMemcpyAsync(J8, s.dJ8, (size_t)s.voxels, cudaMemcpyDeviceToHost, s.s_main));
+    if (J8) CK(down(J8, s.dJ8, (size_t)s.voxels, s.s_main));
     CK(cudaMemcpyAsync(s.hMinMax, s.dMinMax, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.s_main));
     CK(cudaEventRecord(s.ev_time[kEvPerScale * S + 1], s.s_main));
+    if (staged_out) H->stager.drain();        // the workers have moved every piece into the caller's buffers
     H->ran = true;
     return 0;
 }

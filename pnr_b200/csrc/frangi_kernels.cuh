@@ -80,6 +80,9 @@ struct XYParams {
     int seg_h;          // rows per y segment (multiple of 16)
     int nstrips, nsegs;
     int vec_ok;         // rows of I are 4-byte aligned (w % 4 == 0 and base aligned)
+    // Two plane ranges in one launch (the two boundary groups of a slab): launch planes >= zsplit are the planes
+    // zsplit + zgap, ... of I / out.  One range: zsplit = nz, zgap = 0.
+    int zsplit, zgap;
 };
 
 template <int L, bool EXACT>
@@ -95,7 +98,8 @@ gauss_xy_kernel(const __grid_constant__ XYParams p, const __grid_constant__ Gaus
     const int bid = blockIdx.x;
     const int strip = bid % p.nstrips;
     const int seg = (bid / p.nstrips) % p.nsegs;
-    const int z = bid / (p.nstrips * p.nsegs);
+    const int zl = bid / (p.nstrips * p.nsegs);
+    const int z = zl >= p.zsplit ? zl + p.zgap : zl;
     const int x0 = strip * C::TW;
     const int ys = seg * p.seg_h;
     const int ye = min(ys + p.seg_h, p.h);
@@ -303,7 +307,8 @@ gauss_xy_fma_kernel(const __grid_constant__ XYParams p, const __grid_constant__ 
     const int bid = blockIdx.x;
     const int strip = bid % p.nstrips;
     const int seg = (bid / p.nstrips) % p.nsegs;
-    const int z = bid / (p.nstrips * p.nsegs);
+    const int zl = bid / (p.nstrips * p.nsegs);
+    const int z = zl >= p.zsplit ? zl + p.zgap : zl;
     const int x0 = strip * C::TW;
     const int ys = seg * p.seg_h;
     const int ye = min(ys + p.seg_h, p.h);
