@@ -90,3 +90,22 @@ def seed_report(seeds, seeds_ref, dir_deg=1.0):
         if np.degrees(np.arccos(min(1.0, dot))) > dir_deg:
             bad_dir += 1
     return dict(n=len(a), n_ref=len(b), n_common=len(common), match=frac, bad_dir=bad_dir)
+
+
+def direction_gap(oracle, crop, sigmas, zdist, voxel, scale_index):
+    """How well the reference itself determines the direction at `voxel` (z, y, x of `crop`) at scale `scale_index`:
+    (|l2| - |l1|) / |l3| of the reference's eigenvalues of the reference's Hessian there.  The direction written out
+    is the eigenvector of the smallest-magnitude eigenvalue (frangi.cpp:240-250); when |l1| ~ |l2| a last-bit change
+    of the Hessian turns it freely inside the plane of the two (a float-vs-double rebuild
+    of the reference flips such voxels too)."""
+    D = oracle.hessian3d(np.ascontiguousarray(crop), float(sigmas[scale_index]), zdist)
+    z, y, x = voxel
+    A = np.array([[D["Dxx"][z, y, x], D["Dxy"][z, y, x], D["Dxz"][z, y, x]],
+                  [D["Dxy"][z, y, x], D["Dyy"][z, y, x], D["Dyz"][z, y, x]],
+                  [D["Dxz"][z, y, x], D["Dyz"][z, y, x], D["Dzz"][z, y, x]]], np.float64)
+    _, d = oracle.eigen3(A)
+    m = np.abs(d)
+    return float((m[1] - m[0]) / max(m[2], 1e-300))
+
+
+ILL_CONDITIONED_GAP = 2e-3     # (|l2| - |l1|) / |l3| below this: the direction is not determined to 0.5 degrees
