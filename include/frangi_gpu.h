@@ -208,6 +208,19 @@ int frangi_gpu_imerode_z(const uint8_t* I_host, int w, int h, int l, float rad, 
 int frangi_gpu_imdilate(uint8_t* I_host, int w, int h, int l, float rad, int device);
 int frangi_gpu_imgaussian_xy(uint8_t* I_host, int w, int h, int l, float sig, int device);
 
+/* ---- f3, second half: the per-seed correlation score of the plugin's seed filter -------------
+ * Tracker::znccBBB (tracker.cpp:1891-1964) as the plugin calls it for every extracted seed
+ * (Advantra_plugin.cpp:2561-2573, 3-D images): seeds6 = n rows of (x, y, z, vx, vy, vz) as
+ * extractSeeds produced them; corr_out[n] = the score, sig_out[n] (nullable) = the sigma that
+ * scored best.  Bit-identical to the reference (one thread per seed in the reference's operation
+ * order), so the znccth filter and the sort by score that follow decide exactly as the plugin does.
+ * frangi_gpu_seed_zncc scores against the input image the handle holds on its device after
+ * frangi_gpu_run / frangi_gpu_upload (one-slab handles), with the handle's sigmas -- the plugin
+ * passes the same list to the tracker (Advantra_plugin.cpp:2488,2526). */
+int frangi_gpu_seed_zncc(frangi_gpu_t* h, const float* seeds6, int64_t n, float* corr_out, float* sig_out);
+int frangi_gpu_seed_zncc_host(const uint8_t* I_host, int w, int h, int l, const float* sigmas, int nsig,
+                              const float* seeds6, int64_t n, float* corr_out, float* sig_out, int device);
+
 /* ---- utilities --------------------------------------------------------------*/
 void* frangi_gpu_host_alloc(size_t bytes); /* pinned host memory (NULL on failure) */
 void frangi_gpu_host_free(void* p);

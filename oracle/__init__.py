@@ -386,6 +386,23 @@ class Reference:
         f(_p(I, _u8p), w, h, sigma, _p(F, _f32p))
         return F
 
+    @property
+    def has_zncc(self):
+        return hasattr(self.lib, "ref_seed_zncc")
+
+    def seed_zncc(self, I, sigmas, seeds):
+        """Tracker::znccBBB (tracker.cpp:1891-1964) for rows (x, y, z, vx, vy, vz): (corr[n], sigma[n])."""
+        I, w, h, l = _check_vol(I)
+        seeds = np.ascontiguousarray(np.asarray(seeds, np.float32)[:, :6])
+        s = np.ascontiguousarray(sigmas, np.float32)
+        corr = np.empty(len(seeds), np.float32)
+        sig = np.empty(len(seeds), np.float32)
+        f = self.lib.ref_seed_zncc
+        f.restype = None
+        f.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _f32p, C.c_long, _f32p, _f32p]
+        f(_p(I, _u8p), w, h, l, _p(s, _f32p), len(s), _p(seeds, _f32p), len(seeds), _p(corr, _f32p), _p(sig, _f32p))
+        return corr, sig
+
     def unit_directions(self, three_d, ndir):
         out = np.empty((ndir, 3), np.float32)
         f = self.lib.ref_unit_directions

@@ -183,6 +183,28 @@ long ref_extract_seeds(double tolerance, unsigned char* J8, int w, int h, int l,
 }
 
 
+// Tracker::znccBBB for a list of seeds, with the tracker built as the plugin builds it (Advantra_plugin.cpp:2526,
+// README parameters): rows of seeds6 = (x, y, z, vx, vy, vz); corr / sig = the score and the best-scoring sigma
+__attribute__((visibility("default")))
+void ref_seed_zncc(unsigned char* img, int w, int h, int l, const float* sigmas, int nsig, const float* seeds6, long n,
+                   float* corr, float* sig)
+{
+    QuietCout q;
+    FILE* saved_stdout = stdout;
+    FILE* devnull = fopen("/dev/null", "w");
+    if (devnull) stdout = devnull;
+    std::vector<float> sigs(sigmas, sigmas + nsig);
+    Tracker t(sigs, 2, 20, 200, 3.0f, l == 1, 0.3f, 20.0f, 0.8f, 2.0f, 4);
+    for (long i = 0; i < n; ++i) {
+        const float* s = seeds6 + 6 * i;
+        float sg = 0;
+        corr[i] = t.znccBBB(s[0], s[1], s[2], s[3], s[4], s[5], img, w, h, l, sg);
+        sig[i] = sg;
+    }
+    stdout = saved_stdout;
+    if (devnull) fclose(devnull);
+}
+
 // Everything the plugin does downstream of the Frangi filter up to the raw node list, restated from the
 // one call site (Advantra_plugin.cpp) around the UNMODIFIED reference classes:
 //   :2416-2419  node list with the dummy node 0            :2484  smap = 0 (somaradius == 0)

@@ -29,6 +29,7 @@
 #include "seed_kernels.cuh"
 #include "frangi2d_kernels.cuh"
 #include "soma_kernels.cuh"
+#include "zncc_kernels.cuh"
 #include "nccl_dyn.h"
 #include "host_stager.h"
 
@@ -1896,4 +1897,115 @@ FRANGI_API int frangi_gpu_imgaussian_xy(uint8_t* I_host, int w, int h, int l, fl
     CK(cudaGetLastError());
     CK(cudaMemcpy(I_host, d.a, n, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+// ---- f3, second half: the per-seed correlation score of the plugin's seed filter (zncc_kernels.cuh) -------------
+namespace {
+// The template tables of Tracker (tracker.cpp:170-232, 3-D branch), built on the host exactly as the reference's
+// constructor builds them: float loop counters stepping by Vs = max(3 sigma / 12, 1), weights
+// exp(-(u^2 + w^2) / (2 sigma^2)) evaluated in double and stored as float, their mean accumulated in float.
+struct ZnccModel {
+    std::vector<float4> samp;
+    std::vector<int> first;
+    std::vector<float> corrc, sig;
+};
+
+void build_zncc_model(const float* sigmas, int nsig, ZnccModel& m)
+{
+    m.samp.clear(); m.first.assign(1, 0); m.corrc.clear(); m.sig.assign(sigmas, sigmas + nsig);
+    for (int i = 0; i < nsig; ++i) {
+        const float sg = sigmas[i];
+        const int V2 = (int)std::round(1 * sg), U2 = (int)std::round(3 * sg), W2 = (int)std::round(3 * sg);
+        float Vs = (float)((3.0 * sg) / 12);
+        Vs = (Vs < 1.0) ? 1.0f : Vs;
+        std::vector<float> wgt;
+        std::vector<float4> off;
+        float avg = 0.0f;
+        for (float vv = -V2; vv <= V2 + FLT_MIN; vv += Vs)
+            for (float uu = -U2; uu <= U2 + FLT_MIN; uu += Vs)
+                for (float ww = -W2; ww <= W2 + FLT_MIN; ww += Vs) {
+                    const float value = (float)std::exp(-((uu * uu) + (ww * ww)) / (2 * std::pow((double)sg, 2)));
+                    wgt.push_back(value);
+                    off.push_back(make_float4(vv, uu, ww, 0.0f));
+                    avg += value;
+                }
+        avg /= wgt.size();
+        float corrc = 0.0f;
+        for (size_t k = 0; k < wgt.size(); ++k) {
+            const float d = wgt[k] - avg;                          // model2_wgt - model2_avg, a float difference
+            off[k].w = d;
+            corrc = (float)((double)corrc + (double)d * (double)d);  // corrc += pow(d, 2)
+        }
+        m.samp.insert(m.samp.end(), off.begin(), off.end());
+        m.first.push_back((int)m.samp.size());
+        m.corrc.push_back(corrc);
+    }
+}
+
+struct DevZncc {
+    float4* samp = nullptr; int* first = nullptr; float *corrc = nullptr, *sig = nullptr, *seeds = nullptr, *corr = nullptr, *sg = nullptr;
+    uint8_t* img = nullptr;
+    ~DevZncc() { cudaFree(samp); cudaFree(first); cudaFree(corrc); cudaFree(sig); cudaFree(seeds); cudaFree(corr); cudaFree(sg); cudaFree(img); }
+};
+
+int run_zncc(const uint8_t* img_dev, int w, int h, int l, const float* sigmas, int nsig, const float* seeds6, long long n,
+             float* corr_out, float* sig_out, DevZncc& d)
+{
+    if (!seeds6 || !corr_out || n < 0 || nsig < 1) return fail(FRANGI_GPU_EINVAL, "bad argument");
+    if (l < 2) return fail(FRANGI_GPU_EINVAL, "the 2-D template (tracker.cpp:191-207) is not provided: l must be >= 2");
+    if (n == 0) return 0;
+    ZnccModel m;
+    build_zncc_model(sigmas, nsig, m);
+    CK(cudaMalloc(&d.samp, sizeof(float4) * m.samp.size()));
+    CK(cudaMalloc(&d.first, sizeof(int) * m.first.size()));
+    CK(cudaMalloc(&d.corrc, sizeof(float) * nsig));
+    CK(cudaMalloc(&d.sig, sizeof(float) * nsig));
+    CK(cudaMalloc(&d.seeds, sizeof(float) * 6 * (size_t)n));
+    CK(cudaMalloc(&d.corr, sizeof(float) * (size_t)n));
+    CK(cudaMalloc(&d.sg, sizeof(float) * (size_t)n));
+    CK(cudaMemcpy(d.samp, m.samp.data(), sizeof(float4) * m.samp.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.first, m.first.data(), sizeof(int) * m.first.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.corrc, m.corrc.data(), sizeof(float) * nsig, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.sig, m.sig.data(), sizeof(float) * nsig, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.seeds, seeds6, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice));
+    ZnccParams p;
+    p.img = img_dev; p.w = w; p.h = h; p.l = l;
+    p.samp = d.samp; p.first = d.first; p.corrc = d.corrc; p.sig = d.sig; p.nsig = nsig;
+    p.seeds = d.seeds; p.n = n; p.corr_out = d.corr; p.sig_out = d.sg;
+    p.xmax = (float)(w - 1.001); p.ymax = (float)(h - 1.001); p.zmax = (float)(l - 1.001);
+    const long long nb = (n + 127) / 128;
+    if (nb > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "too many seeds");
+    seed_zncc_kernel<<<(unsigned)nb, 128>>>(p);
+    g_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(corr_out, d.corr, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (sig_out) CK(cudaMemcpy(sig_out, d.sg, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+}  // namespace
+
+// the image is the input the handle holds on its device (after frangi_gpu_run / frangi_gpu_upload); one-slab handles
+FRANGI_API int frangi_gpu_seed_zncc(frangi_gpu_t* H, const float* seeds6, int64_t n, float* corr_out, float* sig_out)
+{
+    if (!H) return fail(FRANGI_GPU_EINVAL, "NULL handle");
+    if (H->nslabs_total != 1) return fail(FRANGI_GPU_ESTATE, "seed scoring needs the whole image on one device (one-slab handle)");
+    Slab& s = H->slabs[0];
+    CK(cudaSetDevice(s.dev));
+    RC(sync_all(H));
+    std::vector<float> sig;
+    for (const auto& sp : H->scales) sig.push_back(sp.sigma);
+    DevZncc d;
+    return run_zncc(s.dI, H->w, H->h, H->l, sig.data(), (int)sig.size(), seeds6, n, corr_out, sig_out, d);
+}
+
+FRANGI_API int frangi_gpu_seed_zncc_host(const uint8_t* I_host, int w, int h, int l, const float* sigmas, int nsig,
+                                         const float* seeds6, int64_t n, float* corr_out, float* sig_out, int device)
+{
+    RC(soma_args(I_host, w, h, l, device));
+    if (!sigmas) return fail(FRANGI_GPU_EINVAL, "NULL argument");
+    DevZncc d;
+    const size_t nb = (size_t)w * h * l;
+    CK(cudaMalloc(&d.img, nb));
+    CK(cudaMemcpy(d.img, I_host, nb, cudaMemcpyHostToDevice));
+    return run_zncc(d.img, w, h, l, sigmas, nsig, seeds6, n, corr_out, sig_out, d);
 }

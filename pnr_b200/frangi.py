@@ -79,6 +79,8 @@ SYMBOLS = {
     "frangi_gpu_imerode_z": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _VP, C.c_int]),
     "frangi_gpu_imdilate": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]),
     "frangi_gpu_imgaussian_xy": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]),
+    "frangi_gpu_seed_zncc": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
+    "frangi_gpu_seed_zncc_host": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _VP, C.c_int64, _VP, _VP, C.c_int]),
     "frangi_gpu_host_alloc": (_VP, [C.c_size_t]),
     "frangi_gpu_host_free": (None, [_VP]),
     "frangi_gpu_device_count": (C.c_int, []),
@@ -281,6 +283,14 @@ class FrangiPlan:
         return o
 
 
+    def seed_zncc(self, seeds):
+        """Scores seeds (rows x, y, z, vx, vy, vz) against the input image the handle holds on its device."""
+        seeds = np.ascontiguousarray(np.asarray(seeds, np.float32)[:, :6])
+        corr = np.empty(len(seeds), np.float32)
+        sig = np.empty(len(seeds), np.float32)
+        _check(self.lib.frangi_gpu_seed_zncc(self.handle, _ptr(seeds), len(seeds), _ptr(corr), _ptr(sig)))
+        return corr, sig
+
     def seed_candidates(self, cap=None):
         """Pre-pass of SeedExtractor::extractSeeds (seed.cpp:574-632) on the J8 volume the last run left on the
         device: dict(layer_min u8[l], layer_max u8[l], n_max i32[l], keys i64[sum n_max]) (sorted per layer)."""
@@ -403,6 +413,19 @@ def seed_candidates(J8, device=0):
     _check(lib.frangi_gpu_seed_candidates_host(_ptr(J8), w, h, l, _ptr(lo), _ptr(hi), _ptr(n), _ptr(keys), keys.size,
                                                C.byref(total), device))
     return dict(layer_min=lo, layer_max=hi, n_max=n, keys=keys[:total.value].copy())
+
+
+def seed_zncc(I, sigmas, seeds, device=0):
+    """Tracker::znccBBB for every row (x, y, z, vx, vy, vz) of `seeds` on the raw image I [l][h][w]
+    (Advantra_plugin.cpp:2561-2573): returns (corr[n], sigma[n])."""
+    I, w, h, l = _vol(I)
+    seeds = np.ascontiguousarray(np.asarray(seeds, np.float32)[:, :6])
+    s = np.ascontiguousarray(sigmas, np.float32)
+    corr = np.empty(len(seeds), np.float32)
+    sig = np.empty(len(seeds), np.float32)
+    _check(load_library().frangi_gpu_seed_zncc_host(_ptr(I), w, h, l, s.ctypes.data_as(_f32p), len(s), _ptr(seeds), len(seeds),
+                                                    _ptr(corr), _ptr(sig), device))
+    return corr, sig
 
 
 def imerode(I, rad, device=0):

@@ -139,6 +139,36 @@ def case_g_cold():
                         interp_plane=np.float32(ref.interpz(3, 5, 0.7, F[:1])))
 
 
+def zncc_case(ref, port):
+    """The seeds of a small synthetic volume as extractSeeds produces them, plus crafted ones: off-grid positions, random
+    unit directions, directions along z (the nrm <= 1e-4 branch of tracker.cpp:1895), seeds at the volume's corners and
+    outside it (the clamps of Tracker::interp)."""
+    I = make_volume(96, 80, 24, seed=1, n_neurites=4)
+    sig = [2.0, 4.0, 6.0]
+    R = ref.frangi3d(I, sig, **PARAMS)
+    J8 = port.j_to_j8(R["J"], R["Jmin"], R["Jmax"])
+    seeds = ref.extract_seeds(5.0, J8, R["Vx"], R["Vy"], R["Vz"])[:, :6]
+    rng = np.random.default_rng(12)
+    n = 160
+    pos = rng.uniform([-3, -3, -2], [99, 83, 26], size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:12] = [0, 0, 1]; d[12:20] = [0, 0, -1]; d[20:26] = [1e-5, -2e-5, 1]; d[26:30] = [0, -1, 0]; d[30:34] = [1, 0, 0]
+    pos[:4] = [[0, 0, 0], [95, 79, 23], [0, 79, 0], [95, 0, 23]]
+    crafted = np.concatenate([pos, d], 1).astype(np.float32)
+    allseeds = np.ascontiguousarray(np.concatenate([seeds, crafted], 0), np.float32)
+    return I, sig, allseeds
+
+
+def case_h_zncc():
+    """case H: Tracker::znccBBB, the per-seed score of the plugin's seed filter (Advantra_plugin.cpp:2561-2573)."""
+    ref = Reference()
+    I, sig, seeds = zncc_case(ref, Oracle())
+    corr, best = ref.seed_zncc(I, sig, seeds)
+    np.savez_compressed(os.path.join(OUT, "case_h_zncc.npz"), I=I, sigmas=np.float32(sig), seeds=seeds, corr=corr, sig=best)
+    print("case H:", len(seeds), "seeds, corr in", float(corr.min()), float(corr.max()), "kept at 0.3:", int((corr >= 0.3).sum()))
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"     # "2d" / "soma": only that case (others untouched)
     if which in ("all",):
@@ -149,3 +179,5 @@ if __name__ == "__main__":
         case_f_soma()
     if which in ("all", "cold"):
         case_g_cold()
+    if which in ("all", "zncc"):
+        case_h_zncc()
