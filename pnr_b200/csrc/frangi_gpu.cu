@@ -479,6 +479,9 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
 }
 
 // xy smoothing (K1) of nz dense planes I -> out
+#ifndef XY_FMA_PACKED
+#define XY_FMA_PACKED 1
+#endif
 int launch_xy_planes(const uint8_t* I, float* out, int w, int h, int nz, int fpitch, long long fplane, const ScalePlan& sp,
                      unsigned flags, cudaStream_t st, int zsplit = -1, int zgap = 0)
 {
@@ -489,20 +492,30 @@ int launch_xy_planes(const uint8_t* I, float* out, int w, int h, int nz, int fpi
     p.zsplit = zsplit < 0 ? nz : zsplit; p.zgap = zgap;
     p.fpitch = fpitch; p.fplane = fplane;
     p.nstrips = (w + 255) / 256;
-    // enough CTAs to fill 148 SMs a few times over, else split y into segments
-    const long long want = 148 * 4;
-    const long long per_seg = (long long)p.nstrips * p.nz;
-    int nsegs = (int)std::min<long long>((want + per_seg - 1) / per_seg, (h + 31) / 32);
-    if (nsegs < 1) nsegs = 1;
-    int seg_h = ((h + nsegs - 1) / nsegs + 15) / 16 * 16;
-    p.seg_h = seg_h;
-    p.nsegs = (h + seg_h - 1) / seg_h;
+    // y is split into segments so that the launch fills the GPU.  Each segment redoes the x pass of its 2L halo rows
+    // and a partly filled last wave costs a whole wave (a slab's boundary launch is one or two waves), so the split is
+    // chosen by a small cost model: waves x (rows per segment + halo rows), over a handful of candidates.
+    {
+        const bool fma = (flags & FRANGI_GPU_FLAG_FMA_SMOOTHING) && XY_FMA_PACKED;
+        const long long slots = 148LL * ((fma && sp.rxy_t <= XY_FMA_CTAS3_MAXL) ? 3 : 2);
+        const long long per_seg = (long long)p.nstrips * p.nz;
+        const int cand[] = { 1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32 };
+        double best = 0;
+        int best_h = ((h + 15) / 16) * 16;
+        for (int c : cand) {
+            const int sh = ((h + c - 1) / c + 15) / 16 * 16;
+            if (c > 1 && sh < 32) break;
+            const int ns = (h + sh - 1) / sh;
+            const long long waves = (per_seg * ns + slots - 1) / slots;
+            const double cost = (double)waves * (sh + 2 * sp.rxy + 8);
+            if (best == 0 || cost < best * 0.999) { best = cost; best_h = sh; }
+        }
+        p.seg_h = best_h;
+        p.nsegs = (h + best_h - 1) / best_h;
+    }
     p.vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.I) & 3) == 0);
     const long long nblocks = (long long)p.nstrips * p.nsegs * p.nz;
     if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
-#ifndef XY_FMA_PACKED
-#define XY_FMA_PACKED 1
-#endif
     if (flags & FRANGI_GPU_FLAG_FMA_SMOOTHING)
         return XY_FMA_PACKED ? launch_xy_fma(sp.rxy_t, p, sp.txy, (int)nblocks, st)
                              : launch_xy_e<false>(sp.rxy_t, p, sp.txy, (int)nblocks, st);
