@@ -10,7 +10,7 @@
  * Parity status: PINNED.  The reference ships no tests or golden vectors
  * (SURVEY.md section 4), so the pin is (a) the unmodified reference compiled in
  * place into oracle/_ref/ (oracle/Makefile) and compared bit-for-bit with this
- * file in tests/test_oracle_vs_ref.py, (b) golden fixtures generated from
+ * file in tests/test_oracle_golden.py (test_port_equals_reference_where_built), (b) golden fixtures generated from
  * oracle/_ref and committed under tests/golden/, and (c) the known-answer
  * vectors recorded from the reference in SURVEY.md section 8c.
  *

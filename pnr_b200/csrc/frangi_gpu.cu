@@ -4,10 +4,13 @@
 // tables exactly as the reference does on the host (frangi.cpp:651-680) and
 // launches the kernels of frangi_kernels.cuh.  One `Slab` per device; a handle
 // holds one slab (one-process-per-GPU jobs) or several (one process driving a
-// whole box).  Per scale: xy smoothing of the slab's boundary planes, halo
-// exchange of those planes with the z neighbours (NCCL send/recv on a side
-// stream) overlapped with the xy smoothing of the interior, then the z pass and
-// the fused Hessian/eigen/vesselness/max kernel.
+// whole box).  One slab: per scale xy pass (K1), z pass (K2), Hessian / eigen /
+// vesselness / running max (K3), then the 8-bit map (K4); frangi_gpu_run pipelines
+// upload, kernels and download over z chunks (run_streamed) and moves pageable host
+// buffers through a pinned staging ring (host_stager.h).  Several slabs: the same
+// per slab with the halo exchange of the xy-smoothed boundary planes (NCCL send /
+// recv or peer copies on a side stream) pipelined two scales deep over two Fxy
+// buffers (run_pipeline), then the Jmin / Jmax all-reduce.
 #include "../../include/frangi_gpu.h"
 
 #include <cuda.h>
