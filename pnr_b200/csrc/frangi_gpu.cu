@@ -178,6 +178,63 @@ int launch_xy_fma_t(const XYParams& p, const GaussTaps& t, int nblocks, cudaStre
     return 0;
 }
 
+#ifndef XY_WARP_KERNEL
+#define XY_WARP_KERNEL 1           // FMA mode, radius <= 18: the warp-autonomous form (gauss_xy_warp_kernel)
+#endif
+template <int L>
+int launch_xy_warp_t(const XYWarpParams& p, const GaussTaps& t, cudaStream_t s)
+{
+    using C = XYWarpCfg<L>;
+    auto k = gauss_xy_warp_kernel<L>;
+    static thread_local int configured_dev[64] = { 0 };
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 64 && !configured_dev[dev]) {
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured_dev[dev] = 1;
+    }
+    const long long nblocks = (p.items + C::NW - 1) / C::NW;
+    if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+    k<<<(unsigned)nblocks, 32 * C::NW, C::SMEM_BYTES, s>>>(p, t);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Warps resident per SM of the warp-autonomous form, 0 where the CTA-wide form is used.  Measured at 2048 x 2048 x 512
+// (profiles/r3c): radius 6: 3.26 ms against 3.74 (16 warps per SM, no barrier, FMA pipe 56 %); radius 12: 5.85 against
+// 4.87, radius 18: 9.53 against 6.61 -- the private tiles leave only 11 / 8 warps per SM there, too few to cover the
+// fixed-latency dependencies between the passes.  So: small radii only.
+#ifndef XY_WARP_MAXL
+#define XY_WARP_MAXL 6
+#endif
+int xy_warp_width(int L)
+{
+    if (L > XY_WARP_MAXL) return 0;
+    switch (L) {
+        case 3: return XYWarpCfg<3>::NW;
+        case 6: return XYWarpCfg<6>::NW;
+        case 9: return XYWarpCfg<9>::NW;
+        case 12: return XYWarpCfg<12>::NW;
+        case 15: return XYWarpCfg<15>::NW;
+        case 18: return XYWarpCfg<18>::NW;
+    }
+    return 0;
+}
+
+int launch_xy_warp(int L, const XYWarpParams& p, const GaussTaps& t, cudaStream_t s)
+{
+    switch (L) {
+        case 3: return launch_xy_warp_t<3>(p, t, s);
+        case 6: return launch_xy_warp_t<6>(p, t, s);
+        case 9: return launch_xy_warp_t<9>(p, t, s);
+        case 12: return launch_xy_warp_t<12>(p, t, s);
+        case 15: return launch_xy_warp_t<15>(p, t, s);
+        case 18: return launch_xy_warp_t<18>(p, t, s);
+    }
+    return fail(FRANGI_GPU_EINVAL, "unsupported xy radius %d", L);
+}
+
 int launch_xy_fma(int L, const XYParams& p, const GaussTaps& t, int nblocks, cudaStream_t s)
 {
     switch (L) {
@@ -494,6 +551,30 @@ int launch_xy_planes(const uint8_t* I, float* out, int w, int h, int nz, int fpi
     p.w = w; p.h = h; p.nz = nz;
     p.zsplit = zsplit < 0 ? nz : zsplit; p.zgap = zgap;
     p.fpitch = fpitch; p.fplane = fplane;
+    if (XY_WARP_KERNEL && (flags & FRANGI_GPU_FLAG_FMA_SMOOTHING) && XY_FMA_PACKED && xy_warp_width(sp.rxy_t) > 0) {
+        // warp-autonomous form: items = 64-column strips x y segments x planes, one item per warp
+        XYWarpParams q;
+        q.b = p;
+        q.b.nstrips = (w + 63) / 64;
+        const long long slots = 148LL * xy_warp_width(sp.rxy_t);
+        const long long per_seg = (long long)q.b.nstrips * nz;
+        const int cand[] = { 1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32 };
+        double best = 0;
+        int best_h = ((h + 15) / 16) * 16;
+        for (int c : cand) {
+            const int sh = ((h + c - 1) / c + 15) / 16 * 16;
+            if (c > 1 && sh < 32) break;
+            const int ns = (h + sh - 1) / sh;
+            const long long waves = (per_seg * ns + slots - 1) / slots;
+            const double cost = (double)waves * (sh + 2 * sp.rxy + 8);
+            if (best == 0 || cost < best * 0.999) { best = cost; best_h = sh; }
+        }
+        q.b.seg_h = best_h;
+        q.b.nsegs = (h + best_h - 1) / best_h;
+        q.b.vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.I) & 3) == 0);
+        q.items = (long long)q.b.nstrips * q.b.nsegs * nz;
+        return launch_xy_warp(sp.rxy_t, q, sp.txy, st);
+    }
     p.nstrips = (w + 255) / 256;
     // y is split into segments so that the launch fills the GPU.  Each segment redoes the x pass of its 2L halo rows
     // and a partly filled last wave costs a whole wave (a slab's boundary launch is one or two waves), so the split is

@@ -411,6 +411,187 @@ gauss_xy_fma_kernel(const __grid_constant__ XYParams p, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------
+// K1, FMA mode, warp-autonomous form (radii <= 18): the CTA-wide form above spends its time in barriers at small
+// radii (three __syncthreads per 16-row batch: 3.4 barrier stalls per issue at sigma = 2, FMA pipe 48 % busy).  Here a
+// WARP owns a 64-column strip of one plane and marches down its y segment on its own: private staging tile and
+// private ring of x-passed rows, __syncwarp only.  Same register blocking, twice as deep: in the x pass a lane
+// makes 16 columns x 2 rows (the rows paired in packed registers, staged rows interleaved in pairs so that a 128-bit
+// shared load yields two ready pairs), in the y pass 16 rows x 2 adjacent columns; every shared-memory value feeds up
+// to 16 FFMA2.  Arithmetic per output is the same ascending chain of fused multiply-adds as in gauss_xy_fma_kernel:
+// bit-identical results.  One CTA per SM, as many warps as the per-warp tiles allow (15 / 11 / 8 at radius 6 / 12 / 18).
+// ---------------------------------------------------------------------------
+template <int L>
+struct XYWarpCfg {
+    static constexpr int WS = 64;                              // columns per warp strip
+    static constexpr int RB = 16;
+    static constexpr int LAL = (L + 3) / 4 * 4;
+    static constexpr int PIN0 = WS + 2 * LAL;                  // staged columns per row
+    static constexpr int PINP = ((PIN0 + 13) / 16) * 16 + 2;   // >= PIN0 and = 2 mod 16
+    static constexpr int PP = 2 * PINP;                        // floats per staged row pair: = 4 mod 32 (conflict-free LDS.128)
+    static constexpr int PR = WS + 4;                          // ring row pitch
+    static constexpr int NBLK = 1 + (2 * L + RB - 1) / RB;
+    static constexpr int WARP_FLOATS = (RB / 2) * PP + NBLK * RB * PR;
+    static constexpr int NW0 = (220 * 1024) / (WARP_FLOATS * 4);
+    static constexpr int NW = NW0 > 16 ? 16 : NW0;             // warps per CTA (one CTA per SM)
+    static constexpr int SMEM_BYTES = NW * WARP_FLOATS * 4;
+};
+
+struct XYWarpParams {
+    XYParams b;          // I, out, w, h, nz, fpitch, fplane, seg_h, nsegs, vec_ok, zsplit, zgap; nstrips = strips of 64 columns
+    long long items;     // strips x segments x planes
+};
+
+template <int L>
+__global__ void __launch_bounds__(32 * XYWarpCfg<L>::NW, 1)
+gauss_xy_warp_kernel(const __grid_constant__ XYWarpParams pp, const __grid_constant__ GaussTaps taps)
+{
+    using C = XYWarpCfg<L>;
+    extern __shared__ __align__(16) float smem[];
+    const XYParams& p = pp.b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long item = (long long)blockIdx.x * C::NW + warp;
+    if (item >= pp.items) return;                              // warp-uniform; there is no CTA-wide barrier in this kernel
+    float* s_in2 = smem + warp * C::WARP_FLOATS;
+    float* s_ring = s_in2 + (C::RB / 2) * C::PP;
+    const int strip = (int)(item % p.nstrips);
+    const int seg = (int)((item / p.nstrips) % p.nsegs);
+    const int zl = (int)(item / ((long long)p.nstrips * p.nsegs));
+    const int z = zl >= p.zsplit ? zl + p.zgap : zl;
+    const int x0 = strip * C::WS;
+    const int ys = seg * p.seg_h;
+    const int ye = min(ys + p.seg_h, p.h);
+    const uint8_t* __restrict__ Iz = p.I + (long long)z * p.w * p.h;
+    float* __restrict__ Oz = p.out + (long long)z * p.fplane;
+    const int nb = (ye - ys + C::RB - 1) / C::RB;
+    const int nphases = nb + C::NBLK - 1;
+
+    // staging: a lane fetches the same 4 columns of both rows of a pair (two 32-bit words per unit)
+    constexpr int GROUPS = C::PIN0 / 4;
+    constexpr int UNITS = (C::RB / 2) * GROUPS;
+    constexpr int NU = (UNITS + 31) / 32;
+    uint32_t raw[NU][2];
+    auto fetch = [&](int ph) {
+        const int r0 = ys - L + ph * C::RB;
+#pragma unroll
+        for (int k = 0; k < NU; ++k) {
+            const int idx = lane + 32 * k;
+            uint32_t u[2] = { 0, 0 };
+            if (idx < UNITS) {
+                const int rp = idx / GROUPS;
+                const int g = idx - rp * GROUPS;
+                const int xg = x0 - C::LAL + 4 * g;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int y = clampi(r0 + 2 * rp + q, 0, p.h - 1);
+                    const uint8_t* row = Iz + (long long)y * p.w;
+                    if (p.vec_ok) {
+                        // w is a multiple of 4 and so is xg: a group lies wholly inside the row or wholly beyond one end,
+                        // where all four pixels are the end pixel (replicate clamp) -- ONE load either way, and nothing
+                        // consumes it here (the replication is done at staging time), so the prefetch stays in flight
+                        if (xg >= 0 && xg + 3 < p.w) u[q] = __ldg(reinterpret_cast<const uint32_t*>(row + xg));
+                        else u[q] = (uint32_t)__ldg(row + (xg < 0 ? 0 : p.w - 1));
+                    } else {
+                        u[q] = (uint32_t)__ldg(row + clampi(xg + 0, 0, p.w - 1)) |
+                               ((uint32_t)__ldg(row + clampi(xg + 1, 0, p.w - 1)) << 8) |
+                               ((uint32_t)__ldg(row + clampi(xg + 2, 0, p.w - 1)) << 16) |
+                               ((uint32_t)__ldg(row + clampi(xg + 3, 0, p.w - 1)) << 24);
+                    }
+                }
+            }
+            raw[k][0] = u[0]; raw[k][1] = u[1];
+        }
+    };
+    fetch(0);
+
+    const int xrp = lane & 7;     // x pass: row pair
+    const int xch = lane >> 3;    // x pass: 16-column chunk
+    for (int phase = 0; phase < nphases; ++phase) {
+        __syncwarp();             // the staging tile and the ring block about to be overwritten are no longer read
+#pragma unroll
+        for (int k = 0; k < NU; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < UNITS) {
+                const int rp = idx / GROUPS;
+                const int g = idx - rp * GROUPS;
+                uint32_t a = raw[k][0], b = raw[k][1];
+                const int xg = x0 - C::LAL + 4 * g;
+                if (p.vec_ok && !(xg >= 0 && xg + 3 < p.w)) { a *= 0x01010101u; b *= 0x01010101u; }   // end pixel replicated
+                float* dst = s_in2 + rp * C::PP + 8 * g;
+                *reinterpret_cast<float4*>(dst) = make_float4((float)(a & 0xffu), (float)(b & 0xffu),
+                                                              (float)((a >> 8) & 0xffu), (float)((b >> 8) & 0xffu));
+                *reinterpret_cast<float4*>(dst + 4) = make_float4((float)((a >> 16) & 0xffu), (float)((b >> 16) & 0xffu),
+                                                                  (float)(a >> 24), (float)(b >> 24));
+            }
+        }
+        __syncwarp();
+        if (phase + 1 < nphases) fetch(phase + 1);   // in flight during the x and y passes below
+        // ---- x pass: rows 2*xrp, 2*xrp+1, columns 16*xch .. 16*xch+15 ----
+        {
+            float2 acc[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) acc[o] = make_float2(0.0f, 0.0f);
+            const float4* src = reinterpret_cast<const float4*>(s_in2 + xrp * C::PP + 32 * xch);
+#pragma unroll
+            for (int i2 = 0; i2 < (16 + 2 * C::LAL) / 2; ++i2) {
+                const float4 q = src[i2];
+                const float2 e[2] = { make_float2(q.x, q.y), make_float2(q.z, q.w) };
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int i = 2 * i2 + s2;   // window index: column = x0 + 16*xch + i - LAL
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) {
+                        const int t = i - o - C::LAL + L;
+                        if (t >= 0 && t <= 2 * L) acc[o] = __ffma2_rn(e[s2], make_float2(taps.g[t], taps.g[t]), acc[o]);
+                    }
+                }
+            }
+            float* d0 = s_ring + ((phase % C::NBLK) * C::RB + 2 * xrp) * C::PR + 16 * xch;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                *reinterpret_cast<float4*>(d0 + 4 * q) = make_float4(acc[4 * q].x, acc[4 * q + 1].x, acc[4 * q + 2].x, acc[4 * q + 3].x);
+                *reinterpret_cast<float4*>(d0 + C::PR + 4 * q) = make_float4(acc[4 * q].y, acc[4 * q + 1].y, acc[4 * q + 2].y, acc[4 * q + 3].y);
+            }
+        }
+        const int b = phase - (C::NBLK - 1);     // the batch whose 16 + 2L ring rows are now complete
+        if (b < 0) continue;
+        __syncwarp();
+        // ---- y pass: columns 2*lane, 2*lane+1, output rows ys + b*RB + [0, 16) ----
+        {
+            float2 acc[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) acc[o] = make_float2(0.0f, 0.0f);
+            const float* bp[C::NBLK];
+            int blk = b % C::NBLK;
+#pragma unroll
+            for (int q = 0; q < C::NBLK; ++q) {
+                bp[q] = s_ring + blk * C::RB * C::PR + 2 * lane;
+                blk = (blk + 1 == C::NBLK) ? 0 : blk + 1;
+            }
+#pragma unroll
+            for (int jj = 0; jj < C::RB + 2 * L; ++jj) {
+                const float2 v = *reinterpret_cast<const float2*>(bp[jj / C::RB] + (jj % C::RB) * C::PR);
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    const int t = jj - o;
+                    if (t >= 0 && t <= 2 * L) acc[o] = __ffma2_rn(v, make_float2(taps.g[t], taps.g[t]), acc[o]);
+                }
+            }
+            const int x = x0 + 2 * lane;
+            const int ybase = ys + b * C::RB;
+            if (x + 1 < p.w) {
+#pragma unroll
+                for (int o = 0; o < 16; ++o)
+                    if (ybase + o < ye) *reinterpret_cast<float2*>(Oz + (long long)(ybase + o) * p.fpitch + x) = acc[o];
+            } else if (x < p.w) {
+#pragma unroll
+                for (int o = 0; o < 16; ++o)
+                    if (ybase + o < ye) Oz[(long long)(ybase + o) * p.fpitch + x] = acc[o].x;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K2: z Gaussian pass.  One thread per (x, y) column and chunk of RZ=8 output
 // planes; the 8+2LZ input planes are read with plane stride (coalesced along
 // x) and replicate-clamped against the GLOBAL volume ends (never at slab
