@@ -1045,9 +1045,12 @@ struct HessTile {
     static constexpr int PH = TY + 4;
     static constexpr int PLANE = PW * PH;        // 2640 floats: the TMA box
     static constexpr int SLOT = (PLANE * 4 + 127) / 128 * 32;   // ring slot in floats (TMA destinations are 128-byte aligned)
-    static constexpr int SLOTS = 6;
+#ifndef K3A_STREAM
+#define K3A_STREAM 1        // 1: slot reuse by an empty mbarrier per slot (no __syncthreads in the plane loop, warps drift); 0: round-1 form
+#endif
+    static constexpr int SLOTS = K3A_STREAM ? 7 : 6;
     static constexpr int RING_BYTES = SLOTS * SLOT * 4;
-    static constexpr int SMEM_BYTES = RING_BYTES + SLOTS * 8;   // + one mbarrier per slot (63792)
+    static constexpr int SMEM_BYTES = RING_BYTES + 2 * SLOTS * 8 + 16;   // + a full and an empty mbarrier per slot, issue counter
 };
 
 struct VoxelParams {
@@ -1334,13 +1337,45 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
     const int ze = min(zs + p.zchunk, p.z_begin + p.nz);
     if (zs >= ze) return;
 
-    // plane tiles arrive by TMA (one instruction of thread 0 per plane), see TileRing
+    // plane tiles arrive by TMA (one instruction of one thread per plane), see TileRing
     TileRing<T> tr;
     tr.init(ring, reinterpret_cast<uint64_t*>(ring + T::SLOTS * T::SLOT), tid);
+#if K3A_STREAM
+    // Slot reuse without a CTA-wide barrier: an "empty" mbarrier per slot (NT arrivals: every thread releases plane z-2
+    // after its iteration z) next to the "full" one; planes are issued in order by whichever warp first finds the next
+    // one due and its slot released (compare-and-swap counter), as in the streaming kernel below.  Plane sequence
+    // number n <-> plane zs - 2 + n, slot n % SLOTS, phase n / SLOTS.  Warps may drift SLOTS - 5 planes apart, which
+    // takes them out of lock step: they no longer hit the FP32 and the ALU pipe all at the same time.
+    const uint32_t empty_s = tr.mbar_s + 8 * T::SLOTS;
+    int* s_next = reinterpret_cast<int*>(ring + T::SLOTS * T::SLOT) + 4 * T::SLOTS;
+    const int nseq = (ze - zs) + 4;
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < T::SLOTS; ++k) mbar_init(empty_s + 8 * k, T::NT);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int first = min(T::SLOTS, nseq);
+        for (int n = 0; n < first; ++n) tr.issue(&p.tmap, x0, y0, zs - 2 + n, p.f.base, l);
+        *s_next = first;
+    }
+    __syncthreads();
+    auto issue_seq = [&](int n) {                 // one thread: plane sequence number n into slot n % SLOTS
+        const int slot = n % T::SLOTS, plane = zs - 2 + n;
+        const uint32_t bar = tr.mbar_s + 8 * slot;
+        if (plane < 0 || plane > l - 1) mbar_arrive(bar);
+        else {
+            mbar_expect_tx(bar, T::PLANE * 4);
+            tma_load_3d(tr.ring_s + slot * (T::SLOT * 4), &p.tmap, bar, x0, y0, plane - p.f.base);
+        }
+    };
+#else
     __syncthreads();
     // prologue: planes zs-2 .. zs+2 on their way into the ring; the first four must have landed
     if (tid == 0)
         for (int q = zs - 2; q <= zs + 2; ++q) tr.issue(&p.tmap, x0, y0, q, p.f.base, l);
+#endif
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) tr.wait_next();
 
@@ -1355,8 +1390,21 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
     const long long plane_vox = (long long)h * w;
     long long iz = (long long)(zs - p.z_begin) * plane_vox + xq;   // index of (xq, 0, z) in the own-plane outputs
     for (int z = zs; z < ze; ++z, iz += plane_vox) {
+#if K3A_STREAM
+        if (tx == 0) {                            // issue duty (lane 0 of every warp): planes up to z + SLOTS - 3
+            const int c = z - zs;
+            for (;;) {
+                const int n = *reinterpret_cast<volatile int*>(s_next);
+                if (n >= nseq || n > c + T::SLOTS - 1) break;
+                if (!mbar_test(empty_s + 8 * (n % T::SLOTS), (unsigned)(n / T::SLOTS - 1) & 1u)) break;   // its slot is still in use
+                if (atomicCAS(s_next, n, n + 1) == n) issue_seq(n);
+            }
+        }
+        __syncwarp();
+#else
         __syncthreads();                          // everyone is done with plane z-3's slot
         if (tid == 0 && z + 1 < ze) tr.issue(&p.tmap, x0, y0, z + 3, p.f.base, l);   // lands there while plane z is processed
+#endif
         tr.wait_next();                           // plane z+2 has landed
 
         const bool z_general = z < 2 || z > l - 3;
@@ -1440,6 +1488,11 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
             }
         }
         tr.rotate();
+#if K3A_STREAM
+        // consumer release of plane z-2 (sequence number z - zs): every value this thread loaded from the slot has been
+        // consumed by arithmetic that precedes the arrive in program order
+        mbar_arrive(empty_s + 8 * ((z - zs) % T::SLOTS));
+#endif
     }
     if (MODE == 2) return;
     // warp-shuffle reductions of min (first scale) and max (last scale), one atomic per warp
