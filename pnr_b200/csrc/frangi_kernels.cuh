@@ -1571,8 +1571,24 @@ struct HessTileC {                               // 120 x 8 voxels: one row per 
 struct HessQueue {                               // per warp
     static constexpr int BATCH = 64;             // one packed pair per lane
     static constexpr int CAP = 256;              // power of two >= BATCH - 1 + the 120 entries one plane can add
-    // structure of arrays: field f of entry e at float f * CAP + e; fields = Dxx, Dxy, Dxz, Dyy, Dyz, Dzz, linear voxel offset
-    static constexpr int FIELDS = 7;
+// Issue duty: a warp looks for planes to issue at the top of every (K3C_DUTY + 1)-th iteration.  The SLOWEST warp is the
+// one whose release frees a slot, and it may be the only warp not blocked on a full barrier, so its own checks must
+// keep it supplied: a check at iteration c issues up to sequence number c + AHEAD, iteration c + k needs c + k + 4,
+// hence the period must not exceed AHEAD - 3 (a period of 4 deadlocked on the GPU: every warp waiting for a plane
+// nobody was going to issue).
+#ifndef K3C_DUTY
+#define K3C_DUTY 1
+#endif
+static_assert(K3C_DUTY == 0 || K3C_DUTY == 1, "issue duty period must be 1 or 2");
+static_assert(K3C_DUTY + 1 <= K3C_AHEAD - 3, "issue duty period exceeds the look-ahead");
+#ifndef K3C_AOS
+#define K3C_AOS 0                                // 1: 32-byte entries written with two 128-bit stores (measured 0.6 ms per launch SLOWER); 0: structure of arrays, seven 32-bit stores
+#endif
+    // K3C_AOS: entry e = 8 floats at 8 * e: Dxx, Dxy, Dxz, Dyy | Dyz, Dzz, linear voxel offset, unused.  An append is two
+    // predicated 128-bit stores (8 store instructions per quad instead of 28); a drain gives lane t the entries head + t and
+    // head + 32 + t (a lane stride of 32 bytes: 2-way bank conflicts on the 0.4 drains per plane instead of 4-way).
+    // else: field f of entry e at float f * CAP + e; fields = Dxx, Dxy, Dxz, Dyy, Dyz, Dzz, linear voxel offset
+    static constexpr int FIELDS = K3C_AOS ? 8 : 7;
     static constexpr int WARP_FLOATS = FIELDS * CAP;
     static constexpr int BYTES = (HessTileC::NT / 32) * WARP_FLOATS * 4;
     static constexpr int SMEM_BYTES = HessTileC::RING_BYTES + BYTES + 2 * HessTileC::SLOTS * 8 + 16;   // + full and empty mbarriers, issue counter
@@ -1611,6 +1627,19 @@ __device__ __forceinline__ void queue_append7(uint32_t addr, bool pred, float d0
         "@p st.shared.b32 [%0 + %14], %8;\n\t}"
         ::"r"(addr), "r"((uint32_t)pred), "f"(d0), "f"(d1), "f"(d2), "f"(d3), "f"(d4), "f"(d5), "r"(off),
           "n"(S), "n"(2 * S), "n"(3 * S), "n"(4 * S), "n"(5 * S), "n"(6 * S) : "memory");
+}
+
+// two predicated 128-bit shared stores of one 32-byte queue entry (no branch)
+__device__ __forceinline__ void queue_append_aos(uint32_t addr, bool pred, float d0, float d1, float d2, float d3, float d4,
+                                                 float d5, uint32_t off)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "@p st.shared.v4.f32 [%0], {%2, %3, %4, %5};\n\t"
+        "@p st.shared.v4.b32 [%0 + 16], {%6, %7, %8, %8};\n\t}"
+        ::"r"(addr), "r"((uint32_t)pred), "f"(d0), "f"(d1), "f"(d2), "f"(d3), "r"(__float_as_uint(d4)), "r"(__float_as_uint(d5)),
+          "r"(off) : "memory");
 }
 
 __global__ void __launch_bounds__(HessTileC::NT, 2)
@@ -1720,9 +1749,15 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         typedef Lanes<float2> L2;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
+#if K3C_AOS
+            queue_append_aos(qw_s + 32 * (slot[j] & (Q::CAP - 1)), surv[j],
+                             L2::get(Hxx[j >> 1], j & 1), L2::get(Hxy[j >> 1], j & 1), L2::get(Hxz[j >> 1], j & 1),
+                             L2::get(Hyy[j >> 1], j & 1), L2::get(Hyz[j >> 1], j & 1), L2::get(Hzz[j >> 1], j & 1), off0 + j);
+#else
             queue_append7(qw_s + 4 * (slot[j] & (Q::CAP - 1)), surv[j],
                           L2::get(Hxx[j >> 1], j & 1), L2::get(Hxy[j >> 1], j & 1), L2::get(Hxz[j >> 1], j & 1),
                           L2::get(Hyy[j >> 1], j & 1), L2::get(Hyz[j >> 1], j & 1), L2::get(Hzz[j >> 1], j & 1), off0 + j);
+#endif
     };
 #define PAIR(arr, i) make_float2((arr)[(i)], (arr)[(i) + 1])
 #define DD(hi, mid, lo) vmul(vsub(vsub(hi, mid), vsub(mid, lo)), qs2)
@@ -1798,8 +1833,21 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         have = false;
     };
 
-    // Phase B on this warp's entries [head, head + count), count <= 64: lane t takes entries head + 2t, head + 2t + 1
+    // Phase B on this warp's entries [head, head + count), count <= 64
     auto drain = [&](int count) {
+#if K3C_AOS
+        // lane t takes entries head + t and head + 32 + t
+        const bool has0 = tx < count, two = 32 + tx < count;
+        if (has0) {
+            const float4* q0 = reinterpret_cast<const float4*>(qw + 8 * ((head + tx) & (Q::CAP - 1)));
+            const float4* q1 = reinterpret_cast<const float4*>(qw + 8 * ((head + 32 + tx) & (Q::CAP - 1)));
+            const float4 a0 = q0[0], b0 = q0[1];
+            const float4 a1 = two ? q1[0] : a0, b1 = two ? q1[1] : b0;
+            const float2 f[6] = { make_float2(a0.x, a1.x), make_float2(a0.y, a1.y), make_float2(a0.z, a1.z),
+                                  make_float2(a0.w, a1.w), make_float2(b0.x, b1.x), make_float2(b0.y, b1.y) };
+            const unsigned i0 = __float_as_uint(b0.z), i1 = __float_as_uint(b1.z);
+#else
+        // lane t takes entries head + 2t, head + 2t + 1
         const int o = 2 * tx;
         if (o < count) {
             const bool two = o + 1 < count;
@@ -1808,6 +1856,7 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
 #pragma unroll
             for (int k = 0; k < Q::FIELDS; ++k) f[k] = *reinterpret_cast<const float2*>(e0 + k * Q::CAP);
             const unsigned i0 = __float_as_uint(f[6].x), i1 = two ? __float_as_uint(f[6].y) : i0;
+#endif
             // the stored responses: in flight during the eigen stage
             const float j0 = __ldcg(p.J + i0);
             const float j1 = two ? __ldcg(p.J + i1) : 3.4e38f;
@@ -1840,8 +1889,8 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
 #pragma unroll 1
     for (int c = 0; c < nz; ++c) {                // centre plane z = zs + c; its window = sequence numbers c .. c+4
         const int z = zs + c;
-        // issue duty (see s_next above)
-        if (tx == 0) {
+        // issue duty (see s_next above); every plane is looked at by 8 / (K3C_DUTY + 1) of the warps
+        if (tx == 0 && ((c + wid) & K3C_DUTY) == 0) {
             for (;;) {
                 const int n = *reinterpret_cast<volatile int*>(s_next);
                 if (n >= nseq || n > c + T::AHEAD) break;
