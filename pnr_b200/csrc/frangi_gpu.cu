@@ -799,7 +799,7 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
     long long nblocks = tiles * nzc;
     if (H->w < 5 || H->h < 5 || H->l < 5) nblocks = 0;   // volumes this thin go to the shell kernel entirely
     if (nblocks > 0) { p.nzf = 0; p.n_zface = 0; }       // the tile kernels handle the z faces themselves
-    const long long nshell = p.n_zface + p.n_yface + p.n_xface;
+    long long nshell = p.n_zface + p.n_yface + p.n_xface;
     if (nblocks > 0x7fffffffLL || (nshell + 127) / 128 > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
     if (D) return launch_voxel_t<2>(p, nblocks, nshell, s.s_main);
     if (si == 0) return launch_voxel_t<0>(p, nblocks, nshell, s.s_main);
@@ -812,6 +812,16 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
     // later scale of a bright-ridge run: the compacting kernel (its own 128 x 8 tiling), then the shell
     if (nblocks > 0) {
         p.ntx = (H->w - 2 - HessTileC::X_FIRST + HessTileC::TX - 1) / HessTileC::TX;   // tiles cover x up to w-3
+        // a last tile column that would hold only a few voxel columns costs a full tile's work per warp (2048 wide: 6 of
+        // 120 columns, 1 / 18 of the launch): those columns go to the shell launch below instead
+        const int rem = H->w - 2 - HessTileC::X_FIRST - (p.ntx - 1) * HessTileC::TX;
+        if (K3C_SHELL_REM && p.ntx > 1 && rem <= SHELL_EXTRA_X) {
+            p.ntx -= 1;
+            for (int k = 0; k < rem; ++k) p.xf[p.nxf++] = H->w - 2 - rem + k;
+            p.n_xface = (long long)p.nxf * H->h * p.nz;
+            nshell = p.n_zface + p.n_yface + p.n_xface;
+            if ((nshell + 127) / 128 > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+        }
         p.nty = (H->h + HessTileC::TY - 1) / HessTileC::TY;
         nblocks = (long long)p.ntx * p.nty * nzc;
         if (nblocks > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");

@@ -1053,6 +1053,10 @@ struct HessTile {
     static constexpr int SMEM_BYTES = RING_BYTES + 2 * SLOTS * 8 + 16;   // + a full and an empty mbarrier per slot, issue counter
 };
 
+#ifndef K3C_SHELL_REM
+#define K3C_SHELL_REM 1       // a last tile column of the compacting kernel with <= SHELL_EXTRA_X voxel columns goes to the shell
+#endif
+static constexpr int SHELL_EXTRA_X = 8;
 struct VoxelParams {
     CUtensorMap tmap;     // F as a (w, h, planes) tensor, box = the launching kernel's tile (PW x PH x 1)
     FView f;
@@ -1073,7 +1077,7 @@ struct VoxelParams {
     int* minmax;
     FrangiConsts k;
     // K3b: the face coordinates (deduplicated) and the three region sizes
-    int xf[4], yf[4], zf[4];
+    int xf[4 + SHELL_EXTRA_X], yf[4], zf[4];     // xf: the x faces, then up to SHELL_EXTRA_X columns a tile kernel leaves to the shell
     int nxf, nyf, nzf;
     long long n_zface, n_yface, n_xface;
 };
@@ -1815,7 +1819,57 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     };
 #undef PAIR
 #undef DD
-    // phase A of a plane next to a z face: the general second differences (at most four planes of a volume)
+    // phase A of a plane next to a z face (z < 2 or z > l-3, at most four planes of a volume): the in-plane terms as in
+    // phase_a, the z terms on the clamped planes with the face scales (ZPlanes; the arithmetic of quad_hessians<true>)
+#ifndef K3C_ZFACE_FAST
+#define K3C_ZFACE_FAST 1      // 0: hessian_at_face per voxel (7.5 x the time of an interior plane), for A/B runs
+#endif
+#if K3C_ZFACE_FAST
+    auto phase_a_general = [&](int z, int o0, int o1, int o2, int o3, int o4) {
+        const int o[5] = { o0, o1, o2, o3, o4 };
+        const ZPlanes zp = z_planes(o, z, l, p.k.sigma2);
+        const float* P0 = ring + zp.P0;
+        float c0[4], E[4], a[4], c[4], t2[4], u2[4], ga[4], gc[4];
+        ld4a(c0, P0 + o_own);
+        edges4(c0, E);
+        ld4a(a, P0 + o_own - T::PW); ld4a(c, P0 + o_own + T::PW);
+        ld4a(t2, P0 + o_own - 2 * T::PW); ld4a(u2, P0 + o_own + 2 * T::PW);
+        xdiff_row(a, ga);
+        xdiff_row(c, gc);
+        float pa[4], pb[4], pc[4], pd[4], mm[4], nn[4], gm[4], gn[4], mu[4], md[4], nu[4], nd[4];
+        ld4a(pa, ring + zp.Pa + o_own); ld4a(pb, ring + zp.Pb + o_own);
+        ld4a(pc, ring + zp.Pc + o_own); ld4a(pd, ring + zp.Pd + o_own);
+        ld4a(mm, ring + zp.Pzl + o_own); ld4a(nn, ring + zp.Pzh + o_own);
+        xdiff_row(mm, gm);
+        xdiff_row(nn, gn);
+        ld4a(mu, ring + zp.Pzl + o_own - T::PW); ld4a(md, ring + zp.Pzl + o_own + T::PW);
+        ld4a(nu, ring + zp.Pzh + o_own - T::PW); ld4a(nd, ring + zp.Pzh + o_own + T::PW);
+        const float2 qz2 = make_float2(zp.qz, zp.qz), qzz2 = make_float2(zp.qzz, zp.qzz);
+        const float2 sh2 = make_float2(zp.sh, zp.sh), sl2 = make_float2(zp.sl, zp.sl);
+        float2 Hxx[2], Hxy[2], Hxz[2], Hyy[2], Hyz[2], Hzz[2];
+#define PAIR(arr, i) make_float2((arr)[(i)], (arr)[(i) + 1])
+#define DD(hi, mid, lo) vmul(vsub(vsub(hi, mid), vsub(mid, lo)), qs2)
+        {
+            const float2 hi0 = make_float2(c0[2], c0[3]), hi1 = make_float2(E[2], E[3]);
+            const float2 lo0 = make_float2(E[0], E[1]), lo1 = make_float2(c0[0], c0[1]);
+            Hxx[0] = DD(hi0, lo1, lo0);
+            Hxx[1] = DD(hi1, hi0, lo1);
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int j = 2 * g;
+            Hyy[g] = DD(PAIR(u2, j), PAIR(c0, j), PAIR(t2, j));
+            Hzz[g] = vmul(vsub(vmul(sh2, vsub(PAIR(pa, j), PAIR(pb, j))), vmul(sl2, vsub(PAIR(pc, j), PAIR(pd, j)))), qzz2);
+            Hxy[g] = vmul(vsub(PAIR(gc, j), PAIR(ga, j)), qs2);
+            Hxz[g] = vmul(vsub(PAIR(gn, j), PAIR(gm, j)), qz2);
+            Hyz[g] = vmul(vsub(vsub(PAIR(nd, j), PAIR(nu, j)), vsub(PAIR(md, j), PAIR(mu, j))), qz2);
+        }
+#undef PAIR
+#undef DD
+        test_append(Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
+        have = false;
+    };
+#else
     auto phase_a_general = [&](int z, int o0, int o1, int o2, int o3, int o4) {
         RingField f;
         f.ring = ring; f.o0 = o0; f.o1 = o1; f.o2 = o2; f.o3 = o3; f.o4 = o4;
@@ -1832,6 +1886,7 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         test_append(Hxx, Hxy, Hxz, Hyy, Hyz, Hzz);
         have = false;
     };
+#endif
 
     // Phase B on this warp's entries [head, head + count), count <= 64
     auto drain = [&](int count) {

@@ -30,6 +30,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef EIG_ORDER_C2
+#define EIG_ORDER_C2 0      // 1: keep the (unreachable) middle-value case of the |lambda| ordering, for A/B timing
+#endif
+#ifndef EIG_PACK_ADDS
+#define EIG_PACK_ADDS 1     // 0: the three per-lane adds of the stage as scalar instructions (round-1 form), for A/B timing
+#endif
+
 namespace frangi {
 
 struct FrangiConsts {
@@ -174,12 +181,20 @@ __device__ __forceinline__ void eig_sym3(V a00, V a01, V a02, V a11, V a12, V a2
     // branch-free orthonormal complement of i (Duff, Burgess, Christensen, Hery, Kensler, Liani, Villemin 2017):
     //   s = sign(iz), a = -1/(s+iz), b = ix iy a, u = (1 + s ix^2 a, s b, -s ix), w = (b, s + iy^2 a, -iy)
     V s, a;
+#if EIG_PACK_ADDS
+#pragma unroll
+    for (int k = 0; k < L::N; ++k) L::set(s, k, copysignf(1.0f, L::get(iz, k)));
+    const V nsz = vsub(vneg(s), iz);                     // -(s + iz), one packed add
+#pragma unroll
+    for (int k = 0; k < L::N; ++k) L::set(a, k, mufu_rcp(L::get(nsz, k)));
+#else
 #pragma unroll
     for (int k = 0; k < L::N; ++k) {
         const float sk = copysignf(1.0f, L::get(iz, k));
         L::set(s, k, sk);
         L::set(a, k, -mufu_rcp(sk + L::get(iz, k)));
     }
+#endif
     const V sx = vmul(s, ix), xa = vmul(ix, a), ya = vmul(iy, a);
     const V b = vmul(xa, iy);
     const V ux = vfma(sx, xa, L::bc(1.0f)), uy = vmul(s, b), uz = vneg(sx);
@@ -217,6 +232,7 @@ __device__ __forceinline__ void eig_sym3(V a00, V a01, V a02, V a11, V a12, V a2
     for (int k = 0; k < L::N; ++k) {
         const float fa = L::get(la, k), fb = L::get(lb, k), fi = L::get(lam, k);
         const float e0 = top[k] ? fa : fi, e1 = top[k] ? fb : fa, e2 = top[k] ? fi : fb;
+#if EIG_ORDER_C2
         const float m0 = fabsf(e0), m1 = fabsf(e1), m2 = fabsf(e2);
         const bool c1 = m0 >= m1 && m0 > m2;            // e0 has the largest magnitude
         const bool c2 = !c1 && m1 >= m0 && m1 > m2;     // else e1 has
@@ -228,6 +244,18 @@ __device__ __forceinline__ void eig_sym3(V a00, V a01, V a02, V a11, V a12, V a2
         L::set(out.l2, k, sw ? x : y);
         // where the isolated eigenvalue went: it is e2 if top (x when c1, y when c2), else e0 (x unless c1)
         sel_i[k] = top[k] ? ((c1 && !sw) || (c2 && sw)) : (!c1 && !sw);
+#else
+        // For an ascending triple the middle value never has the strictly largest magnitude (frangi.cpp:1289-1296 can
+        // only pick e1 when |e1| >= |e0| and |e1| > |e2|, i.e. e0 = e1 < 0, and then the first rule has already taken
+        // e0), and |e0| > |e2| implies |e0| >= |e1|: the largest is e0 if |e0| > |e2|, else e2.
+        const bool c1 = fabsf(e0) > fabsf(e2);
+        const float x = c1 ? e2 : e0;
+        const bool sw = fabsf(x) > fabsf(e1);
+        L::set(out.l3, k, c1 ? e0 : e2);
+        L::set(out.l1, k, sw ? e1 : x);
+        L::set(out.l2, k, sw ? x : e1);
+        sel_i[k] = !sw && (c1 == top[k]);    // the isolated eigenvalue is e2 if top (it is x when c1), else e0 (x unless c1)
+#endif
     }
     }
     // null vector of (M - l1 I) in (u, w) coordinates, from the larger row
@@ -237,9 +265,14 @@ __device__ __forceinline__ void eig_sym3(V a00, V a01, V a02, V a11, V a12, V a2
     for (int k = 0; k < L::N; ++k) {
         const float g0 = L::get(f0, k), g1 = L::get(f1, k), mk = L::get(m01, k);
         const bool r0 = fabsf(g0) >= fabsf(g1);
-        L::set(y0, k, (r0 ? -mk : g1) + 1e-18f);   // the epsilon turns the all-zero case (la == lb) into (1, 0)
+#if EIG_PACK_ADDS
+        L::set(y0, k, r0 ? -mk : g1);
+#else
+        L::set(y0, k, (r0 ? -mk : g1) + 1e-18f);
+#endif
         L::set(y1, k, r0 ? g0 : -mk);
     }
+    if (EIG_PACK_ADDS) y0 = vadd(y0, L::bc(1e-18f));     // the epsilon turns the all-zero case (la == lb) into (1, 0)
     const V nrm = vfma(y0, y0, vmul(y1, y1));
     V sn;
 #pragma unroll
@@ -317,7 +350,8 @@ __device__ __forceinline__ V vesselness(const EigT<V>& e, const FrangiConsts& c)
     const V xa = vmul(Ra2, L::bc(-1.4426950408889634f * c.inv_2a2));
     V tRa;
 #pragma unroll
-    for (int k = 0; k < L::N; ++k) L::set(tRa, k, 1.0f - mufu_ex2(L::get(xa, k)));
+    for (int k = 0; k < L::N; ++k) L::set(tRa, k, EIG_PACK_ADDS ? mufu_ex2(L::get(xa, k)) : 1.0f - mufu_ex2(L::get(xa, k)));
+    if (EIG_PACK_ADDS) tRa = vsub(L::bc(1.0f), tRa);
     const V xb = vmul(Rb2, L::bc(-1.4426950408889634f * c.inv_2b2));
     V tRb;
 #pragma unroll
