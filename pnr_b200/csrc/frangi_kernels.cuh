@@ -742,8 +742,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef MBAR_HINT_NS
+#define MBAR_HINT_NS 0        // > 0: suspend-time hint of try_wait (measured at 20000: no effect on any kernel)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
+#if MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"((uint32_t)MBAR_HINT_NS) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -751,6 +763,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)      // non-blocking: has the phase completed?
 {
