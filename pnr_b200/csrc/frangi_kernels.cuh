@@ -1559,22 +1559,28 @@ hessian_eigen_kernel(const __grid_constant__ VoxelParams p)
 //  * each warp has its own survivor queue (no shared counter, no atomics): slots come from ballots, a drain runs
 //    whenever the warp has 64 survivors (one packed pair per lane);
 //  * tiles are 16-byte aligned with the quads: a row segment of a quad is ONE 128-bit load with a lane stride of
-//    16 bytes, the columns next to a quad come from the neighbour lanes by shuffle, and lanes 0 / 31 only carry
-//    the halo (a tile is 120 columns wide), so there is no edge-lane special case at all;
+//    16 bytes, the columns next to a quad come from the neighbour lanes by shuffle; the outer half of the quads
+//    of lanes 0 / 31 is the halo (a tile is 124 columns wide: box columns 2 .. 125), which a per-voxel mask covers,
+//    so there is no edge-lane special case at all;
 //  * a lane keeps its own row of the planes z-2 .. z+2 and the x first differences of z-1 .. z+1 in register
 //    rings rotated by renaming (the plane loop dispatches on z mod 5 to five instantiations of phase A);
 //  * survivors carry their 32-bit linear voxel offset; the stored response is gathered at the drain.
 // Same operations on the same operands in the same order as quad_hessians<false>: bit-identical second differences.
-struct HessTileC {                               // 120 x 8 voxels: one row per warp, one quad per lane, lanes 0 / 31 halo only
-    static constexpr int TX = 120, TY = 8, NT = 256;
-    static constexpr int XH = 4;                 // halo columns each side (one quad)
+struct HessTileC {                               // 124 x 8 voxels: one row per warp, one quad per lane
+#ifndef K3C_TX
+#define K3C_TX 124                               // 120: lanes 0 / 31 carry only halo (the first round-2 form), for A/B runs
+#endif
+    static constexpr int TX = K3C_TX, TY = 8, NT = 256;
+    static_assert(TX == 124 || TX == 120, "tile width");
+    static constexpr int XH = (128 - TX) / 2;    // halo columns each side: half a quad (of lanes 0 and 31), or a whole one
     static constexpr int PW = TX + 2 * XH;       // 128 floats per tile row
     static constexpr int PH = TY + 4;
     static constexpr int PLANE = PW * PH;        // 1536 floats: the TMA box
     static constexpr int SLOT = PLANE;           // 6144 bytes (a multiple of 128)
     static constexpr int SLOTS = 8;              // = warps: warp s refills slot s
     static constexpr int RING_BYTES = SLOTS * SLOT * 4;
-    static constexpr int X_FIRST = 0;            // tile bx covers the voxels x = TX * bx + [0, TX); x = 0, 1 are masked (shell)
+    static constexpr int X_FIRST = XH == 2 ? 2 : 0;   // tile bx covers the voxels x = X_FIRST + TX * bx + [0, TX): TX 124 starts at the
+                                                 // first interior column 2; TX 120 at 0 with x = 0, 1 masked (shell)
 #ifndef K3C_AHEAD
 #define K3C_AHEAD 6
 #endif
@@ -1587,7 +1593,7 @@ struct HessTileC {                               // 120 x 8 voxels: one row per 
 };
 struct HessQueue {                               // per warp
     static constexpr int BATCH = 64;             // one packed pair per lane
-    static constexpr int CAP = 256;              // power of two >= BATCH - 1 + the 120 entries one plane can add
+    static constexpr int CAP = 256;              // power of two >= BATCH - 1 + the 124 entries one plane can add
 // Issue duty: a warp looks for planes to issue at the top of every (K3C_DUTY + 1)-th iteration.  The SLOWEST warp is the
 // one whose release frees a slot, and it may be the only warp not blocked on a full barrier, so its own checks must
 // keep it supplied: a check at iteration c issues up to sequence number c + AHEAD, iteration c + k needs c + k + 4,
@@ -1676,7 +1682,8 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
     const int bx = bid % p.ntx; bid /= p.ntx;
     const int by = bid % p.nty;
     const int bz = bid / p.nty;
-    const int x0 = bx * T::TX - T::XH, y0 = by * T::TY - 2;   // global coordinates of tile entry (0, 0); x0 is a multiple of 4 floats (TMA)
+    const int x0 = bx * T::TX + T::X_FIRST - T::XH, y0 = by * T::TY - 2;   // global coordinates of tile entry (0, 0); x0 is a multiple of 4 floats (TMA)
+    static_assert((T::X_FIRST - T::XH) % 4 == 0 && T::TX % 4 == 0, "TMA: the innermost box coordinate must be a multiple of 16 bytes");
     const int w = p.f.w, h = p.f.h, l = p.f.l;
     const int zs = p.z_begin + bz * p.zchunk;
     const int ze = min(zs + p.zchunk, p.z_begin + p.nz);
@@ -1709,12 +1716,13 @@ hessian_eigen_compact_kernel(const __grid_constant__ VoxelParams p)
         *s_next = first;
     }
     __syncthreads();
-    const int xq = x0 + 4 * tx;                   // first voxel of the lane's quad (lanes 0 and 31: halo only)
+    const int xq = x0 + 4 * tx;                   // first voxel of the lane's quad (lanes 0 and 31: half or all of it is halo)
     const int yrow = by * T::TY + wid;            // the warp's row
-    const bool row_ok = yrow >= 2 && yrow <= h - 3 && tx >= 1 && tx <= 30;
+    const bool row_ok = yrow >= 2 && yrow <= h - 3;
     bool m[4];                                    // voxel j of the quad is an interior voxel of this tile
 #pragma unroll
-    for (int j = 0; j < 4; ++j) m[j] = row_ok && xq + j >= 2 && xq + j <= w - 3;
+    for (int j = 0; j < 4; ++j)
+        m[j] = row_ok && 4 * tx + j >= T::XH && 4 * tx + j < T::XH + T::TX && xq + j >= 2 && xq + j <= w - 3;
     const int o_own = (wid + 2) * T::PW + 4 * tx; // tile entry of (xq, yrow)
     const float qs = 0.25f * p.k.sigma2;
     const float2 qs2 = make_float2(qs, qs);

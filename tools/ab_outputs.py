@@ -13,6 +13,8 @@ CASES = [  # w, h, l, sigmas, flags
     (300, 200, 40, [2., 4., 6.], 0),
     (2048, 72, 24, [2., 4.], 1),       # the width whose last tile column holds six voxel columns
     (250, 64, 9, [1., 2., 3.], 1),
+    (257, 40, 12, [2., 3.], 1),        # (w - 4) mod 124 = 5: the last five interior columns go to the shell
+    (128, 24, 10, [1., 2.], 1),        # a single, partly filled tile column
 ]
 
 
