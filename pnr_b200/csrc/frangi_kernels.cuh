@@ -978,20 +978,43 @@ __device__ __forceinline__ float d_dz(const Field& f, int x, int y, int z)
     return __fmul_rn(face_scale(z, f.l), __fsub_rn(f.at(x, y, min(z + 1, f.l - 1)), f.at(x, y, max(z - 1, 0))));
 }
 
+// All 24 taps are loaded before the first difference is formed, so that a thread waits for memory once, not once per
+// group of terms (the shell kernel is bound by the latency of these loads; same operations on the same operands as
+// the nested d_dx / d_dy / d_dz form above).
 template <class Field>
 __device__ __noinline__ Hess hessian_at_face(const Field& f, int x, int y, int z, float sigma2)
 {
-    const int xl = max(x - 1, 0), xh = min(x + 1, f.w - 1);
-    const int yl = max(y - 1, 0), yh = min(y + 1, f.h - 1);
-    const int zl = max(z - 1, 0), zh = min(z + 1, f.l - 1);
+    const int W = f.w - 1, Hh = f.h - 1, L = f.l - 1;
+    const int xl = max(x - 1, 0), xh = min(x + 1, W);
+    const int yl = max(y - 1, 0), yh = min(y + 1, Hh);
+    const int zl = max(z - 1, 0), zh = min(z + 1, L);
+    const int xm = max(x - 1, 0), xp = min(x + 1, W), ym = max(y - 1, 0), yp = min(y + 1, Hh), zm = max(z - 1, 0), zp = min(z + 1, L);
+    // d/dx at (xh, y, z), (xl, y, z), (x, yh, z), (x, yl, z), (x, y, zh), (x, y, zl): hi and lo tap of each
+    const float x0h = f.at(min(xh + 1, W), y, z), x0l = f.at(max(xh - 1, 0), y, z);
+    const float x1h = f.at(min(xl + 1, W), y, z), x1l = f.at(max(xl - 1, 0), y, z);
+    const float x2h = f.at(xp, yh, z), x2l = f.at(xm, yh, z);
+    const float x3h = f.at(xp, yl, z), x3l = f.at(xm, yl, z);
+    const float x4h = f.at(xp, y, zh), x4l = f.at(xm, y, zh);
+    const float x5h = f.at(xp, y, zl), x5l = f.at(xm, y, zl);
+    // d/dy at (x, yh, z), (x, yl, z), (x, y, zh), (x, y, zl)
+    const float y0h = f.at(x, min(yh + 1, Hh), z), y0l = f.at(x, max(yh - 1, 0), z);
+    const float y1h = f.at(x, min(yl + 1, Hh), z), y1l = f.at(x, max(yl - 1, 0), z);
+    const float y2h = f.at(x, yp, zh), y2l = f.at(x, ym, zh);
+    const float y3h = f.at(x, yp, zl), y3l = f.at(x, ym, zl);
+    // d/dz at (x, y, zh), (x, y, zl)
+    const float z0h = f.at(x, y, min(zh + 1, L)), z0l = f.at(x, y, max(zh - 1, 0));
+    const float z1h = f.at(x, y, min(zl + 1, L)), z1l = f.at(x, y, max(zl - 1, 0));
     const float sx = face_scale(x, f.w), sy = face_scale(y, f.h), sz = face_scale(z, f.l);
+    const float sxh = face_scale(xh, f.w), sxl = face_scale(xl, f.w);
+    const float syh = face_scale(yh, f.h), syl = face_scale(yl, f.h);
+    const float szh = face_scale(zh, f.l), szl = face_scale(zl, f.l);
     Hess H;
-    H.xx = __fmul_rn(__fmul_rn(sx, __fsub_rn(d_dx(f, xh, y, z), d_dx(f, xl, y, z))), sigma2);
-    H.xy = __fmul_rn(__fmul_rn(sy, __fsub_rn(d_dx(f, x, yh, z), d_dx(f, x, yl, z))), sigma2);
-    H.xz = __fmul_rn(__fmul_rn(sz, __fsub_rn(d_dx(f, x, y, zh), d_dx(f, x, y, zl))), sigma2);
-    H.yy = __fmul_rn(__fmul_rn(sy, __fsub_rn(d_dy(f, x, yh, z), d_dy(f, x, yl, z))), sigma2);
-    H.yz = __fmul_rn(__fmul_rn(sz, __fsub_rn(d_dy(f, x, y, zh), d_dy(f, x, y, zl))), sigma2);
-    H.zz = __fmul_rn(__fmul_rn(sz, __fsub_rn(d_dz(f, x, y, zh), d_dz(f, x, y, zl))), sigma2);
+    H.xx = __fmul_rn(__fmul_rn(sx, __fsub_rn(__fmul_rn(sxh, __fsub_rn(x0h, x0l)), __fmul_rn(sxl, __fsub_rn(x1h, x1l)))), sigma2);
+    H.xy = __fmul_rn(__fmul_rn(sy, __fsub_rn(__fmul_rn(sx, __fsub_rn(x2h, x2l)), __fmul_rn(sx, __fsub_rn(x3h, x3l)))), sigma2);
+    H.xz = __fmul_rn(__fmul_rn(sz, __fsub_rn(__fmul_rn(sx, __fsub_rn(x4h, x4l)), __fmul_rn(sx, __fsub_rn(x5h, x5l)))), sigma2);
+    H.yy = __fmul_rn(__fmul_rn(sy, __fsub_rn(__fmul_rn(syh, __fsub_rn(y0h, y0l)), __fmul_rn(syl, __fsub_rn(y1h, y1l)))), sigma2);
+    H.yz = __fmul_rn(__fmul_rn(sz, __fsub_rn(__fmul_rn(sy, __fsub_rn(y2h, y2l)), __fmul_rn(sy, __fsub_rn(y3h, y3l)))), sigma2);
+    H.zz = __fmul_rn(__fmul_rn(sz, __fsub_rn(__fmul_rn(szh, __fsub_rn(z0h, z0l)), __fmul_rn(szl, __fsub_rn(z1h, z1l)))), sigma2);
     return H;
 }
 
@@ -2249,8 +2272,9 @@ hessian_eigen_shell_kernel(const __grid_constant__ VoxelParams p)
     }
     float jv = 0.0f;
     if (active) {
-        const Hess H = hessian_at_face(p.f, x, y, z, p.k.sigma2);
         const long long i = ((long long)(z - p.z_begin) * h + y) * w + x;
+        if (MODE == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.J + i));    // the stored response: in flight beside the taps
+        const Hess H = hessian_at_face(p.f, x, y, z, p.k.sigma2);
         if (MODE == 2) {
             p.D[0][i] = H.zz; p.D[1][i] = H.yy; p.D[2][i] = H.yz;
             p.D[3][i] = H.xx; p.D[4][i] = H.xy; p.D[5][i] = H.xz;
@@ -2263,13 +2287,17 @@ hessian_eigen_shell_kernel(const __grid_constant__ VoxelParams p)
         float mn = active ? jv : 3.4e38f;
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
-        if ((threadIdx.x & 31) == 0 && mn < 3.0e38f) atomicMin(p.minmax + 0, __float_as_int(mn));
+        // one atomic per warp on ONE address serialises in L2 (262 144 warps: the launch took as long as the atomics);
+        // min / max only ever move one way, so a warp whose value cannot change the result (a plain read says so) skips it
+        if ((threadIdx.x & 31) == 0 && mn < 3.0e38f && __float_as_int(mn) < *reinterpret_cast<volatile int*>(p.minmax + 0))
+            atomicMin(p.minmax + 0, __float_as_int(mn));
     }
     {
         float mx = active ? jv : 0.0f;
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-        if ((threadIdx.x & 31) == 0) atomicMax(p.minmax + 1, __float_as_int(mx));
+        if ((threadIdx.x & 31) == 0 && __float_as_int(mx) > *reinterpret_cast<volatile int*>(p.minmax + 1))
+            atomicMax(p.minmax + 1, __float_as_int(mx));
     }
 }
 
