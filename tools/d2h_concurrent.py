@@ -24,14 +24,17 @@ def main():
     d_up = torch.empty(up, dtype=torch.uint8, device="cuda")
     d_down = torch.empty(down, dtype=torch.uint8, device="cuda")
     h_up.fill_(1); h_down.fill_(1); d_down.fill_(2)
+    s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
     times = []
     for it in range(6):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        d_up.copy_(h_up, non_blocking=True)
-        h_down.copy_(d_down, non_blocking=True)
+        with torch.cuda.stream(s_up):             # both directions at once, as the chunk-pipelined call moves them
+            d_up.copy_(h_up, non_blocking=True)
+        with torch.cuda.stream(s_down):
+            h_down.copy_(d_down, non_blocking=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], device="cuda")

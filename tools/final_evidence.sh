@@ -23,7 +23,7 @@ for r in rows[2:]:
     n = r[h.index('Kernel Name')]
     if 'hessian_eigen_kernel' in n and a is None: a = r[h.index('ID')]
     if 'hessian_eigen_compact' in n: c = r[h.index('ID')]
-print(a, c)")
+print(int(a) + 1, int(c) + 1)   # --kernel-id counts invocations from 1")
 python tools/k3_executed.py $REP $IDS > profiles/${TAG}_k3_executed.txt
 for k in hessian_eigen_compact_kernel "hessian_eigen_kernelILi0ELb0" hessian_eigen_shell_kernelILi0 gauss_xy_warp_kernelILi6 "gauss_z_tma_kernelILi9ELb0"; do
   echo "== $k"
