@@ -157,6 +157,9 @@ def test_frangi3d_config1_256x256x64(oracle):
     ((24, 80, 96), [2.0, 4.0, 6.0], 2.0, True),        # dark ridges
     ((16, 64, 64), [3.0], 2.0, False),                 # single scale
     ((2, 2, 2), [2.0], 2.0, False),                    # smallest legal volume
+    ((10, 20, 257), [2.0, 3.0], 2.0, False),           # (w - 4) mod 124 = 5: the streaming kernel leaves its last five columns to the shell
+    ((8, 12, 132), [1.0, 2.0], 2.0, False),            # one tile column + a four-column remainder
+    ((5, 24, 140), [1.0, 2.0], 2.0, False),            # every plane but one lies next to a z face (the z-face form of the tile kernels)
 ])
 def test_frangi3d_edge_cases(oracle, shape, sigs, zdist, bw):
     l, h, w = shape
