@@ -812,11 +812,12 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
 #else
     if (s.voxels >= (1LL << 32)) return launch_voxel_t<1, true>(p, nblocks, nshell, s.s_main);  // survivors carry 32-bit voxel offsets
 #endif
-    // later scale of a bright-ridge run: the compacting kernel (its own 128 x 8 tiling), then the shell
+    // later scale of a bright-ridge run: the compacting kernel (its own 124 x 8 tiling), then the shell
     if (nblocks > 0) {
         p.ntx = (H->w - 2 - HessTileC::X_FIRST + HessTileC::TX - 1) / HessTileC::TX;   // tiles cover x up to w-3
-        // a last tile column that would hold only a few voxel columns costs a full tile's work per warp (2048 wide: 6 of
-        // 120 columns, 1 / 18 of the launch): those columns go to the shell launch below instead
+        // a last tile column that would hold only a few voxel columns costs a full tile's work per warp (with 120-column
+        // tiles a 2048-wide volume had 6 columns in its 18th tile column: 1 / 18 of the launch): those columns go to the
+        // shell launch below instead
         const int rem = H->w - 2 - HessTileC::X_FIRST - (p.ntx - 1) * HessTileC::TX;
         if (K3C_SHELL_REM && p.ntx > 1 && rem <= SHELL_EXTRA_X) {
             p.ntx -= 1;
