@@ -458,11 +458,18 @@ def run_ours(a, sigmas, w, h, l):
             hV = [PinnedBuffer((nz, h, w), np.uint8) for _ in range(3)]
             hIe = hI.array
         k_e2e = a.e2e_steps or min(a.steps, 5)
-        plan.run(hIe, J=hJ.array, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array)   # warm-up
+        # --outputs: the extra arrays the handle keeps come back too, into buffers of the same kind (without these the
+        # Python mirror would allocate fresh pageable arrays inside every timed call)
+        Buf = _Plain if a.pageable else PinnedBuffer
+        hS = Buf((nz, h, w), np.uint8) if (flags & pnr_b200.FLAG_SCALE_IDX) else None
+        hD = Buf((3, nz, h, w), np.float32) if (flags & pnr_b200.FLAG_DIR_F32) else None
+        extra_out = dict(scale=hS.array if hS else None, direction=hD.array if hD else None)
+        extra_bytes = (1 if hS else 0) + (12 if hD else 0)
+        plan.run(hIe, J=hJ.array, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array, **extra_out)   # warm-up
         barrier()
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            r = plan.run(hIe, J=hJ.array, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array)
+            r = plan.run(hIe, J=hJ.array, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array, **extra_out)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         te = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -470,7 +477,7 @@ def run_ours(a, sigmas, w, h, l):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dt = float(te.item())
         e2e = {"value": total_vox * k_e2e / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(total_vox), "d2h_bytes_per_step": int(total_vox * 7 + 8 * world),
+               "h2d_bytes_per_step": int(total_vox), "d2h_bytes_per_step": int(total_vox * (7 + extra_bytes) + 8 * world),
                "steps": k_e2e, "ms_per_step": 1e3 * dt / k_e2e,
                "call": "frangi_gpu_run(I_host -> J_host f32, Jmin, Jmax, Vx, Vy, Vz host u8), "
                        + ("pageable" if a.pageable else "pinned") + " host buffers",
@@ -478,15 +485,15 @@ def run_ours(a, sigmas, w, h, l):
         # the same call as the caller really needs it (J is freed at once, Advantra_plugin.cpp:2514): J8 + V only
         if world == 1 and not a.pageable:
             hJ8 = PinnedBuffer((nz, h, w), np.uint8)
-            plan.run(hI.array, J=None, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array, J8=hJ8.array, want_J=False)
+            plan.run(hI.array, J=None, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array, J8=hJ8.array, want_J=False, **extra_out)
             barrier()
             t0 = time.perf_counter()
             for _ in range(k_e2e):
-                plan.run(hI.array, J=None, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array, J8=hJ8.array, want_J=False)
+                plan.run(hI.array, J=None, Vx=hV[0].array, Vy=hV[1].array, Vz=hV[2].array, J8=hJ8.array, want_J=False, **extra_out)
             torch.cuda.synchronize()
             dt8 = time.perf_counter() - t0
             e2e["j8_variant"] = {"value": total_vox * k_e2e / dt8, "unit": UNIT, "ms_per_step": 1e3 * dt8 / k_e2e,
-                                 "d2h_bytes_per_step": int(total_vox * 4 + 8),
+                                 "d2h_bytes_per_step": int(total_vox * (4 + extra_bytes) + 8),
                                  "call": "frangi_gpu_run(I_host -> J8, Vx, Vy, Vz host u8; J_host = NULL)"}
             hJ8.free()
         # the buffers as the unmodified call site passes them (new float[size], Advantra_plugin.cpp:2490-2494): pageable
@@ -494,17 +501,19 @@ def run_ours(a, sigmas, w, h, l):
             pJ = np.zeros((nz, h, w), np.float32)
             pV = [np.zeros((nz, h, w), np.uint8) for _ in range(3)]
             pI = np.array(hI.array)
-            plan.run(pI, J=pJ, Vx=pV[0], Vy=pV[1], Vz=pV[2])
+            p_extra = dict(scale=np.zeros((nz, h, w), np.uint8) if hS else None,
+                           direction=np.zeros((3, nz, h, w), np.float32) if hD else None)
+            plan.run(pI, J=pJ, Vx=pV[0], Vy=pV[1], Vz=pV[2], **p_extra)
             t0 = time.perf_counter()
             kp = min(k_e2e, 2)
             for _ in range(kp):
-                plan.run(pI, J=pJ, Vx=pV[0], Vy=pV[1], Vz=pV[2])
+                plan.run(pI, J=pJ, Vx=pV[0], Vy=pV[1], Vz=pV[2], **p_extra)
             torch.cuda.synchronize()
             dtp = time.perf_counter() - t0
             e2e["pageable"] = {"value": total_vox * kp / dtp, "unit": UNIT, "ms_per_step": 1e3 * dtp / kp, "steps": kp,
                                "call": "the same call with ordinary (pageable) host buffers"}
-            del pJ, pV, pI
-        for b in [hJ] + hV:
+            del pJ, pV, pI, p_extra
+        for b in [hJ] + hV + [x for x in (hS, hD) if x is not None]:
             b.free()
 
     # ---- the extractSeeds pre-pass on the J8 volume the last run left on the device ----------
