@@ -449,3 +449,47 @@ class Reference:
             raise RuntimeError(f"ref_trace rc={rc} counts={c}")
         return dict(seeds=seeds[:c[1]].copy(), nodes=nodes[:c[2]].copy(), nbr=nbr[:c[3]].copy(),
                     n_extracted=c[0], n_traces=c[4])
+
+
+PLUGIN_REF_SO = os.path.join(_HERE, "_ref", "libpnr_plugin_ref.so")
+PLUGIN_GPU_SO = os.path.join(_HERE, "_ref", "libpnr_plugin_gpu.so")
+
+
+class Plugin:
+    """The reference's WHOLE plugin translation unit (Advantra_plugin.cpp, unmodified, against the Qt / Vaa3D stand-ins of
+    oracle/stubs/; oracle/plugin_wrap.cpp), driven through its batch entry point Advantra::dofunc("advantra_func").
+    arm = "ref": the reference's own Frangi; arm = "gpu": the same unchanged call site with the drop-in class Frangi of
+    pnr_b200/csrc/frangi.h (needs a GPU at run time).  Everything the plugin writes lands under `workdir`."""
+
+    PARAMS = ("2,4,6", "0", "5", "0.3", "3", "2", "200", "20", "2", "4", "1")     # the README's usage line
+
+    def __init__(self, arm: str = "ref"):
+        path = dict(ref=PLUGIN_REF_SO, gpu=PLUGIN_GPU_SO)[arm]
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.arm = arm
+        self.lib = C.CDLL(path)
+        self.lib.plugin_run.restype = C.c_int
+        self.lib.plugin_run.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_int,
+                                        C.c_int, C.c_int, C.c_int]
+
+    @staticmethod
+    def available(arm: str = "ref") -> bool:
+        return os.path.exists(dict(ref=PLUGIN_REF_SO, gpu=PLUGIN_GPU_SO)[arm])
+
+    def run(self, I, workdir, params=None, save_midres=True, single_tree=True, max_traces=0, name="img"):
+        """Runs the plugin on I[l][h][w]; returns {file name without the prefix: text} for every file it wrote."""
+        I, w, h, l = _check_vol(I)
+        p = [str(v) for v in (params or self.PARAMS)]
+        arr = (C.c_char_p * len(p))(*[s.encode() for s in p])
+        prefix = os.path.join(str(workdir), name)
+        n = self.lib.plugin_run(_p(I, _u8p), w, h, l, prefix.encode(), arr, len(p), int(save_midres), int(single_tree),
+                                int(max_traces))
+        if n < 0:
+            raise RuntimeError("Advantra::dofunc refused the arguments")
+        out = {}
+        for f in sorted(os.listdir(str(workdir))):
+            if f.startswith(name):
+                with open(os.path.join(str(workdir), f)) as fh:
+                    out[f[len(name):]] = fh.read()
+        return out
