@@ -453,18 +453,23 @@ class Reference:
 
 PLUGIN_REF_SO = os.path.join(_HERE, "_ref", "libpnr_plugin_ref.so")
 PLUGIN_GPU_SO = os.path.join(_HERE, "_ref", "libpnr_plugin_gpu.so")
+PLUGIN_REPLAY_SO = os.path.join(_HERE, "_ref", "libpnr_plugin_replay.so")
+_PLUGIN_SO = dict(ref=PLUGIN_REF_SO, gpu=PLUGIN_GPU_SO, replay=PLUGIN_REPLAY_SO)
 
 
 class Plugin:
     """The reference's WHOLE plugin translation unit (Advantra_plugin.cpp, unmodified, against the Qt / Vaa3D stand-ins of
     oracle/stubs/; oracle/plugin_wrap.cpp), driven through its batch entry point Advantra::dofunc("advantra_func").
     arm = "ref": the reference's own Frangi; arm = "gpu": the same unchanged call site with the drop-in class Frangi of
-    pnr_b200/csrc/frangi.h (needs a GPU at run time).  Everything the plugin writes lands under `workdir`."""
+    pnr_b200/csrc/frangi.h (needs a GPU at run time); arm = "replay": the call site is handed filter outputs the caller
+    supplies (run(..., replay=(J8, Vx, Vy, Vz))) -- outputs captured on a GPU box, or the reference's own with some
+    eigenvector signs turned -- every other Frangi member being the reference's.  Everything the plugin writes lands
+    under `workdir`."""
 
     PARAMS = ("2,4,6", "0", "5", "0.3", "3", "2", "200", "20", "2", "4", "1")     # the README's usage line
 
     def __init__(self, arm: str = "ref"):
-        path = dict(ref=PLUGIN_REF_SO, gpu=PLUGIN_GPU_SO)[arm]
+        path = _PLUGIN_SO[arm]
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.arm = arm
@@ -475,11 +480,20 @@ class Plugin:
 
     @staticmethod
     def available(arm: str = "ref") -> bool:
-        return os.path.exists(dict(ref=PLUGIN_REF_SO, gpu=PLUGIN_GPU_SO)[arm])
+        return os.path.exists(_PLUGIN_SO[arm])
 
-    def run(self, I, workdir, params=None, save_midres=True, single_tree=True, max_traces=0, name="img"):
+    def run(self, I, workdir, params=None, save_midres=True, single_tree=True, max_traces=0, name="img", replay=None):
         """Runs the plugin on I[l][h][w]; returns {file name without the prefix: text} for every file it wrote."""
         I, w, h, l = _check_vol(I)
+        if (self.arm == "replay") != (replay is not None):
+            raise ValueError("replay arrays go with the replay arm, and only with it")
+        if replay is not None:
+            keep = [np.ascontiguousarray(v, np.uint8) for v in replay]
+            if len(keep) != 4 or any(v.shape != I.shape for v in keep):
+                raise ValueError("replay = (J8, Vx, Vy, Vz), each of the volume's shape")
+            self.lib.plugin_set_replay.restype = None
+            self.lib.plugin_set_replay.argtypes = [_u8p] * 4
+            self.lib.plugin_set_replay(*[_p(v, _u8p) for v in keep])
         p = [str(v) for v in (params or self.PARAMS)]
         arr = (C.c_char_p * len(p))(*[s.encode() for s in p])
         prefix = os.path.join(str(workdir), name)

@@ -10,11 +10,17 @@
 //                               up front and the `Frangi` the plugin names is the drop-in class of pnr_b200/csrc/frangi.h
 //                               (libfrangi_shim.so -> the C-ABI -> the CUDA kernels).  Nothing else differs: this is the
 //                               swap INTEGRATION.md describes, made on the unchanged call site.
-// tests/test_plugin_e2e.py runs both on the same volume and compares the SWC files they write.
+//   _ref/libpnr_plugin_replay.so  with -DPNR_PLUGIN_REPLAY_FRANGI: the reference's frangi.h / frangi.cpp under the class
+//                               name RefFrangi (a -DFrangi=RefFrangi compile of the unmodified files), and a `Frangi`
+//                               derived from it whose frangi3d hands back arrays the test supplied (plugin_set_replay):
+//                               filter outputs captured on the GPU box, or the reference's own outputs with some
+//                               eigenvector signs turned, go through the unmodified plugin on a CPU-only host.
+// tests/test_plugin_e2e.py runs them on the same volume and compares the SWC files they write.
 //
 // The "image file" the plugin loads is a volume the test handed over (plugin_run below); SWC files are written as
 // plain text (one "n type x y z r parent" row per record, the Vaa3D layout); images the plugin saves are dropped.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <string>
@@ -28,6 +34,33 @@
 #ifdef PNR_PLUGIN_GPU_FRANGI
 #include "../pnr_b200/csrc/frangi.h"      // class Frangi = the drop-in
 #define FRANGI3D_H                        // the reference's frangi.h (same directory as the plugin source): skipped
+#endif
+
+#ifdef PNR_PLUGIN_REPLAY_FRANGI
+#define Frangi RefFrangi
+#include "frangi.h"                       // the reference's header (-I$(REF)); its include guard is now set
+#undef Frangi
+namespace { const unsigned char* g_replay[4] = { 0, 0, 0, 0 }; }     // J8, Vx, Vy, Vz of the volume plugin_run is given
+class Frangi : public RefFrangi {
+public:
+    Frangi(std::vector<float> s, float zd, float a, float b, float c, float b1, float b2) : RefFrangi(s, zd, a, b, c, b1, b2) {}
+    // The plugin keeps of J only its 8-bit form round((J-Jmin)/(Jmax-Jmin)*255) (Advantra_plugin.cpp:2499-2512), then
+    // deletes J: with Jmin = 0, Jmax = 255 and J = the supplied byte that conversion returns the byte.
+    void frangi3d(unsigned char*, int w, int h, int l, float* J, float& Jmin, float& Jmax, unsigned char* Vx,
+                  unsigned char* Vy, unsigned char* Vz)
+    {
+        if (!g_replay[0]) { fprintf(stderr, "plugin_set_replay was not called\n"); abort(); }
+        const long long n = (long long)w * h * l;
+        for (long long i = 0; i < n; ++i) J[i] = (float)g_replay[0][i];
+        memcpy(Vx, g_replay[1], (size_t)n); memcpy(Vy, g_replay[2], (size_t)n); memcpy(Vz, g_replay[3], (size_t)n);
+        Jmin = 0.f; Jmax = 255.f;
+    }
+};
+extern "C" __attribute__((visibility("default")))
+void plugin_set_replay(const unsigned char* J8, const unsigned char* Vx, const unsigned char* Vy, const unsigned char* Vz)
+{
+    g_replay[0] = J8; g_replay[1] = Vx; g_replay[2] = Vy; g_replay[3] = Vz;
+}
 #endif
 
 #include "Advantra_plugin.cpp"
