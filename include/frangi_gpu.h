@@ -58,7 +58,15 @@ enum {
      * eigen stage of the previous one; needs a second pair of intermediate buffers
      * (+8 B/voxel).  Results are bit-identical.  Off by default: measured gain 1.7 %
      * (DESIGN.md section 6), and multi-slab handles do not have it. */
-    FRANGI_GPU_FLAG_OVERLAP_Z = 16
+    FRANGI_GPU_FLAG_OVERLAP_Z = 16,
+    /* Direction bytes with the reference's SIGN.  The reference writes column 0 of what its double-precision
+     * Householder / QL solver returns (frangi.cpp:198,239-250,1269-1495): the sign of that eigenvector is an
+     * accident of the iteration, and the closed form of the fast path returns the other one in half of the voxels
+     * (same axis within 0.5 degrees).  With this flag every voxel a scale wins is re-solved on the device with the
+     * reference's own algorithm in double precision, operation for operation, and Vx/Vy/Vz (and the float direction)
+     * are the reference's: byte-identical with bit-exact smoothing, except where the arg-max scale itself is a tie.
+     * J, Jmin, Jmax, J8 are unaffected.  Costs a double-precision pass per scale (an opt-in parity mode). */
+    FRANGI_GPU_FLAG_REFERENCE_DIRECTION = 32
 };
 
 /* ---- whole-volume handle, one process driving ndev devices ---------------

@@ -531,7 +531,7 @@ int alloc_slab(frangi_gpu* H, Slab& s, int dev, int index, int zb, int ze)
     CK(cudaMalloc(&s.dVy, (size_t)s.voxels));
     CK(cudaMalloc(&s.dVz, (size_t)s.voxels));
     CK(cudaMalloc(&s.dJ8, (size_t)s.voxels));
-    if (H->flags & FRANGI_GPU_FLAG_SCALE_IDX) CK(cudaMalloc(&s.dScale, (size_t)s.voxels));
+    if (H->flags & (FRANGI_GPU_FLAG_SCALE_IDX | FRANGI_GPU_FLAG_REFERENCE_DIRECTION)) CK(cudaMalloc(&s.dScale, (size_t)s.voxels));
     if (H->flags & FRANGI_GPU_FLAG_DIR_F32) CK(cudaMalloc(&s.dDir, sizeof(float) * 3 * (size_t)s.voxels));
     CK(cudaMalloc(&s.dMinMax, 2 * sizeof(int)));
     CK(cudaHostAlloc(&s.hMinMax, 2 * sizeof(int), cudaHostAllocDefault));
@@ -769,9 +769,8 @@ int face_list(int n, int lo, int hi, int* out)
 }
 
 // mode 0 / 1: vesselness update of scale si; mode 2: dump the six second differences into D
-int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* const* D = nullptr)
+int launch_voxel_core(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* const* D, VoxelParams& p)
 {
-    VoxelParams p;
     p.tmap = s.tmF;
     p.f = make_fview(H, s);
     p.J = s.dJ; p.Vx = s.dVx; p.Vy = s.dVy; p.Vz = s.dVz;
@@ -843,6 +842,22 @@ int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* con
         CK(cudaGetLastError());
     }
     return launch_voxel_t<1>(p, 0, nshell, s.s_main);
+}
+
+// The Hessian / eigen stage of scale si on slab s; with FRANGI_GPU_FLAG_REFERENCE_DIRECTION followed by the pass that
+// rewrites the direction of every voxel this scale has just won with the reference's own solver (K9).
+int launch_voxel(frangi_gpu* H, Slab& s, const ScalePlan& sp, int si, float* const* D = nullptr)
+{
+    VoxelParams p;
+    RC(launch_voxel_core(H, s, sp, si, D, p));
+    if (!D && (H->flags & FRANGI_GPU_FLAG_REFERENCE_DIRECTION) && s.voxels > 0) {
+        const long long nb = (s.voxels + 127) / 128;
+        if (nb > 0x7fffffffLL) return fail(FRANGI_GPU_EINVAL, "grid too large");
+        reference_direction_kernel<<<(unsigned)nb, 128, 0, s.s_main>>>(p);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
+    return 0;
 }
 
 // Exchange the xy-smoothed boundary planes of every local slab with its z

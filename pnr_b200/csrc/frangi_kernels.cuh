@@ -23,6 +23,7 @@
 #include <stdint.h>
 
 #include "frangi_voxel_math.cuh"
+#include "ref_eigen.h"
 
 namespace frangi {
 
@@ -2298,6 +2299,46 @@ hessian_eigen_shell_kernel(const __grid_constant__ VoxelParams p)
         for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
         if ((threadIdx.x & 31) == 0 && __float_as_int(mx) > *reinterpret_cast<volatile int*>(p.minmax + 1))
             atomicMax(p.minmax + 1, __float_as_int(mx));
+    }
+}
+
+// K9 reference_direction_kernel (FRANGI_GPU_FLAG_REFERENCE_DIRECTION), after the K3 launches of a scale.
+// The direction the reference writes is column 0 of what its double-precision Householder / QL solver returns
+// (frangi.cpp:198, 239-250, 1269-1495) -- an eigenvector whose SIGN is whatever that iteration ends on.  The closed form
+// of K3 returns the same axis (within 0.5 degrees) with the other sign in half of the voxels, and downstream code is not
+// indifferent to it (tests/test_plugin_e2e.py).  This pass re-derives, for every voxel whose running maximum scale `p.scale`
+// has just taken (scale_idx == p.scale; on the first scale: every voxel), the second differences with the reference's
+// face rules from F, runs the reference's solver on them (ref_eigen.h, rdouble: separately rounded double operations in
+// the reference's order) and writes the reference's three direction bytes, round(((v + 1) / 2) * 255) in double.  With
+// bit-exact smoothing the second differences are the reference's bit for bit, hence so are the bytes.  One thread per
+// voxel from global memory, double precision: an opt-in parity mode, not the fast path.
+__global__ void __launch_bounds__(128)
+reference_direction_kernel(const __grid_constant__ VoxelParams p)
+{
+    const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (i >= p.voxels) return;
+    if (p.scale_idx[i] != (uint8_t)p.scale) return;
+    const int w = p.f.w, h = p.f.h;
+    const int x = (int)(i % w);
+    const long long row = i / w;
+    const int y = (int)(row % h);
+    const int z = p.z_begin + (int)(row / h);
+    const Hess H = hessian_at_face(p.f, x, y, z, p.k.sigma2);
+    rdouble A[3][3], V[3][3], d[3];
+    A[0][0] = rdouble((double)H.xx); A[0][1] = rdouble((double)H.xy); A[0][2] = rdouble((double)H.xz);
+    A[1][0] = rdouble((double)H.xy); A[1][1] = rdouble((double)H.yy); A[1][2] = rdouble((double)H.yz);
+    A[2][0] = rdouble((double)H.xz); A[2][1] = rdouble((double)H.yz); A[2][2] = rdouble((double)H.zz);
+    ref_eigen_decomposition(A, V, d);
+    uint8_t code[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const rdouble t = ((V[c][0] + rdouble(1.0)) / rdouble(2.0)) * rdouble(255.0);
+        const double r = round(t.v);                               // half away from zero, as the C library's
+        code[c] = r >= 255.0 ? (uint8_t)255 : (r > 0.0 ? (uint8_t)(int)r : (uint8_t)0);      // NaN -> 0 (x86: INT_MIN, clamped)
+    }
+    p.Vx[i] = code[0]; p.Vy[i] = code[1]; p.Vz[i] = code[2];
+    if (p.dir) {
+        p.dir[i] = (float)V[0][0].v; p.dir[p.voxels + i] = (float)V[1][0].v; p.dir[2 * p.voxels + i] = (float)V[2][0].v;
     }
 }
 

@@ -1,6 +1,7 @@
 // frangi_shim.cpp -- the Frangi class of frangi.h on top of the C-ABI (include/frangi_gpu.h).
 #include "frangi.h"
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -11,11 +12,19 @@ namespace {
 {
     throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + frangi_gpu_last_error());
 }
+// The reference's constructor has no place for flags, and a call site compiled unchanged cannot set the public field:
+// the environment variable PNR_FRANGI_FLAGS (a sum of FRANGI_GPU_FLAG_* values) supplies the initial value of `flags`,
+// e.g. 32 = the reference's eigenvector signs, 1 = fused multiply-add smoothing.  Unset: 0 (bit-exact smoothing).
+unsigned initial_flags()
+{
+    const char* e = std::getenv("PNR_FRANGI_FLAGS");
+    return e && *e ? (unsigned)std::strtoul(e, nullptr, 0) : 0u;
+}
 }  // namespace
 
 Frangi::Frangi(std::vector<float> sigs, float zdist_, float alpha_, float beta_, float C_, float beta_one, float beta_two)
     : sig(sigs), zdist(zdist_), alpha(alpha_), beta(beta_), BetaOne(beta_one), BetaTwo(beta_two), C(C_),
-      blackwhite(false), flags(0), handle_(nullptr), hw_(0), hh_(0), hl_(0), hz_(0), ha_(0), hb_(0), hc_(0),
+      blackwhite(false), flags(initial_flags()), handle_(nullptr), hw_(0), hh_(0), hl_(0), hz_(0), ha_(0), hb_(0), hc_(0),
       hbw_(false), hflags_(0)
 {
 }

@@ -8,6 +8,7 @@
 #include <cmath>
 
 #include "frangi.h"
+#include "ref_eigen.h"
 
 unsigned char Frangi::ndirs2d = 30;   // frangi.cpp:24
 unsigned char Frangi::ndirs3d = 90;   // frangi.cpp:25
@@ -94,184 +95,9 @@ float Frangi::interpz(int x, int y, float z, float* img, int w, int h, int l)
     return (1 - t) * v_lo + t * v_hi;
 }
 
-// ---- symmetric 3x3 eigen-decomposition in double (frangi.cpp:1230-1495) -----------------------------------------
-double Frangi::hypot2(double x, double y) { return std::sqrt(x * x + y * y); }
-
-// Householder reduction of the symmetric matrix held in V to tridiagonal form (EISPACK tred2): on return d holds
-// the diagonal, e[1..2] the sub-diagonal and V the accumulated orthogonal transformation.
-void Frangi::tred2(double V[3][3], double d[3], double e[3])
-{
-    const int N = 3;
-    for (int c = 0; c < N; ++c) d[c] = V[N - 1][c];
-    for (int i = N - 1; i >= 1; --i) {
-        double norm1 = 0.0, hsum = 0.0;
-        for (int k = 0; k < i; ++k) norm1 = norm1 + std::fabs(d[k]);
-        if (norm1 == 0.0) {
-            e[i] = d[i - 1];
-            for (int c = 0; c < i; ++c) {
-                d[c] = V[i - 1][c];
-                V[i][c] = 0.0;
-                V[c][i] = 0.0;
-            }
-        } else {
-            for (int k = 0; k < i; ++k) {
-                d[k] /= norm1;
-                hsum += d[k] * d[k];
-            }
-            const double last = d[i - 1];
-            double root = std::sqrt(hsum);
-            if (last > 0) root = -root;
-            e[i] = norm1 * root;
-            hsum = hsum - last * root;
-            d[i - 1] = last - root;
-            for (int c = 0; c < i; ++c) e[c] = 0.0;
-            for (int c = 0; c < i; ++c) {            // similarity transform of the leading block
-                const double dc = d[c];
-                V[c][i] = dc;
-                double acc = e[c] + V[c][c] * dc;
-                for (int k = c + 1; k <= i - 1; ++k) {
-                    acc += V[k][c] * d[k];
-                    e[k] += V[k][c] * dc;
-                }
-                e[c] = acc;
-            }
-            double dot = 0.0;
-            for (int c = 0; c < i; ++c) {
-                e[c] /= hsum;
-                dot += e[c] * d[c];
-            }
-            const double half = dot / (hsum + hsum);
-            for (int c = 0; c < i; ++c) e[c] -= half * d[c];
-            for (int c = 0; c < i; ++c) {
-                const double dc = d[c], ec = e[c];
-                for (int k = c; k <= i - 1; ++k) V[k][c] -= (dc * e[k] + ec * d[k]);
-                d[c] = V[i - 1][c];
-                V[i][c] = 0.0;
-            }
-        }
-        d[i] = hsum;
-    }
-    for (int i = 0; i < N - 1; ++i) {                // accumulate the transformations
-        V[N - 1][i] = V[i][i];
-        V[i][i] = 1.0;
-        const double hh = d[i + 1];
-        if (hh != 0.0) {
-            for (int k = 0; k <= i; ++k) d[k] = V[k][i + 1] / hh;
-            for (int c = 0; c <= i; ++c) {
-                double acc = 0.0;
-                for (int k = 0; k <= i; ++k) acc += V[k][i + 1] * V[k][c];
-                for (int k = 0; k <= i; ++k) V[k][c] -= acc * d[k];
-            }
-        }
-        for (int k = 0; k <= i; ++k) V[k][i + 1] = 0.0;
-    }
-    for (int c = 0; c < N; ++c) {
-        d[c] = V[N - 1][c];
-        V[N - 1][c] = 0.0;
-    }
-    V[N - 1][N - 1] = 1.0;
-    e[0] = 0.0;
-}
-
-// Implicit-shift QL on the tridiagonal matrix (EISPACK tql2), eigenvectors accumulated in V, then eigenvalues and
-// vectors sorted ascending by value (first minimum wins).
-void Frangi::tql2(double V[3][3], double d[3], double e[3])
-{
-    const int N = 3;
-    for (int i = 1; i < N; ++i) e[i - 1] = e[i];
-    e[N - 1] = 0.0;
-    double shift_total = 0.0, scale_ref = 0.0;
-    const double eps = std::pow(2.0, -52.0);
-    for (int lo = 0; lo < N; ++lo) {
-        const double cand = std::fabs(d[lo]) + std::fabs(e[lo]);
-        scale_ref = scale_ref > cand ? scale_ref : cand;
-        int m = lo;
-        while (m < N) {
-            if (std::fabs(e[m]) <= eps * scale_ref) break;
-            ++m;
-        }
-        if (m > lo) {
-            do {
-                double g = d[lo];
-                double p = (d[lo + 1] - g) / (2.0 * e[lo]);
-                double r = hypot2(p, 1.0);
-                if (p < 0) r = -r;
-                d[lo] = e[lo] / (p + r);
-                d[lo + 1] = e[lo] * (p + r);
-                const double dl1 = d[lo + 1];
-                double h = g - d[lo];
-                for (int i = lo + 2; i < N; ++i) d[i] -= h;
-                shift_total = shift_total + h;
-                p = d[m];
-                double c = 1.0, c2 = c, c3 = c;
-                const double el1 = e[lo + 1];
-                double s = 0.0, s2 = 0.0;
-                for (int i = m - 1; i >= lo; --i) {
-                    c3 = c2;
-                    c2 = c;
-                    s2 = s;
-                    g = c * e[i];
-                    h = c * p;
-                    r = hypot2(p, e[i]);
-                    e[i + 1] = s * r;
-                    s = e[i] / r;
-                    c = p / r;
-                    p = c * d[i] - s * g;
-                    d[i + 1] = h + s * (c * g + s * d[i]);
-                    for (int k = 0; k < N; ++k) {
-                        h = V[k][i + 1];
-                        V[k][i + 1] = s * V[k][i] + c * h;
-                        V[k][i] = c * V[k][i] - s * h;
-                    }
-                }
-                p = -s * s2 * c3 * el1 * e[lo] / dl1;
-                e[lo] = s * p;
-                d[lo] = c * p;
-            } while (std::fabs(e[lo]) > eps * scale_ref);
-        }
-        d[lo] = d[lo] + shift_total;
-        e[lo] = 0.0;
-    }
-    for (int i = 0; i < N - 1; ++i) {
-        int best = i;
-        double pv = d[i];
-        for (int j = i + 1; j < N; ++j)
-            if (d[j] < pv) { best = j; pv = d[j]; }
-        if (best != i) {
-            d[best] = d[i];
-            d[i] = pv;
-            for (int r = 0; r < N; ++r) {
-                const double t = V[r][i];
-                V[r][i] = V[r][best];
-                V[r][best] = t;
-            }
-        }
-    }
-}
-
-namespace {
-void swap_pair(double V[3][3], double d[3], double mag[3], int a, int b)
-{
-    double t = d[a]; d[a] = d[b]; d[b] = t;
-    t = mag[a]; mag[a] = mag[b]; mag[b] = t;
-    for (int r = 0; r < 3; ++r) { t = V[r][a]; V[r][a] = V[r][b]; V[r][b] = t; }
-}
-}  // namespace
-
-// A symmetric -> columns of V = unit eigenvectors, d ordered |d0| <= |d1| <= |d2| with the reference's tie rules
-// (frangi.cpp:1284-1304): the largest magnitude goes last (`>=` against the other candidate, `>` against the last
-// slot), then the first two are swapped on a strict `>`.
-void Frangi::eigen_decomposition_static(double A[3][3], double V[3][3], double d[3])
-{
-    double e[3], mag[3];
-    for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) V[r][c] = A[r][c];
-    tred2(V, d, e);
-    tql2(V, d, e);
-    for (int k = 0; k < 3; ++k) mag[k] = absd(d[k]);
-    if (mag[0] >= mag[1] && mag[0] > mag[2]) swap_pair(V, d, mag, 0, 2);
-    else if (mag[1] >= mag[0] && mag[1] > mag[2]) swap_pair(V, d, mag, 1, 2);
-    if (mag[0] > mag[1]) swap_pair(V, d, mag, 0, 1);
-}
-
+// ---- symmetric 3x3 eigen-decomposition in double (frangi.cpp:1230-1495): ref_eigen.h, shared with the device ---------
+double Frangi::hypot2(double x, double y) { return re_hypot(x, y); }
+void Frangi::tred2(double V[3][3], double d[3], double e[3]) { ref_tred2(V, d, e); }
+void Frangi::tql2(double V[3][3], double d[3], double e[3]) { ref_tql2(V, d, e); }
+void Frangi::eigen_decomposition_static(double A[3][3], double V[3][3], double d[3]) { ref_eigen_decomposition(A, V, d); }
 void Frangi::eigen_decomposition(double A[3][3], double V[3][3], double d[3]) { eigen_decomposition_static(A, V, d); }

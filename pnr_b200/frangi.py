@@ -31,6 +31,7 @@ FLAG_DIR_F32 = 2
 FLAG_SCALE_IDX = 4
 FLAG_LOCAL_HALO = 8
 FLAG_OVERLAP_Z = 16
+FLAG_REFERENCE_DIRECTION = 32      # Vx / Vy / Vz with the reference's eigenvector sign (include/frangi_gpu.h)
 
 _u8p = C.POINTER(C.c_uint8)
 _f32p = C.POINTER(C.c_float)

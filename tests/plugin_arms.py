@@ -17,16 +17,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_arm(arm, I, params, max_traces, workdir=None, timeout=3600, replay=None):
+def run_arm(arm, I, params, max_traces, workdir=None, timeout=3600, replay=None, env=None):
     """-> dict(files={suffix: text}, seconds=wall time of dofunc, log=the plugin's stdout).
-    replay = (J8, Vx, Vy, Vz) for arm "replay": the filter outputs the plugin's call site is handed."""
+    replay = (J8, Vx, Vy, Vz) for arm "replay": the filter outputs the plugin's call site is handed.
+    env: extra environment of the child, e.g. PNR_FRANGI_FLAGS for the drop-in class (pnr_b200/csrc/frangi_shim.cpp)."""
     workdir = workdir or tempfile.mkdtemp(prefix=f"pnr_plugin_{arm}_")
     vol = os.path.join(workdir, "_vol.npy")
     np.save(vol, np.ascontiguousarray(I, np.uint8))
     if replay is not None:
         np.save(os.path.join(workdir, "_replay.npy"), np.stack([np.ascontiguousarray(v, np.uint8) for v in replay]))
     cmd = [sys.executable, "-m", "tests.plugin_arms", arm, vol, workdir, str(int(max_traces))] + [str(p) for p in params]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, errors="replace", timeout=timeout)
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, errors="replace", timeout=timeout,
+                         env=dict(os.environ, **env) if env else None)
     os.remove(vol)
     if replay is not None:
         os.remove(os.path.join(workdir, "_replay.npy"))
