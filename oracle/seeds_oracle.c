@@ -15,8 +15,10 @@
  * pixel or the image border; otherwise one seed is emitted at the member of the
  * equal-height plateau nearest to the plateau's centroid.
  *
- * Parity status: PINNED against oracle/_ref (the compiled reference) in
- * tests/test_oracle_vs_ref.py; bit-exact seed positions are required.
+ * Parity status: PINNED against the compiled reference: tests/test_oracle_golden.py
+ * (test_case_b_outputs_and_seeds: the seed list of tests/golden/case_b_seeds.npz, generated
+ * from oracle/_ref by tools/make_golden.py; test_port_equals_reference_where_built: against
+ * oracle/_ref directly); bit-exact seed positions are required.
  */
 #include <float.h>
 #include <math.h>

@@ -2,10 +2,14 @@
 against stand-ins for Qt and the Vaa3D API (oracle/plugin_wrap.cpp, oracle/stubs/) and driven through its batch entry
 point Advantra::dofunc("advantra_func") -- image load, Frangi (Advantra_plugin.cpp:2488-2512), seeds, correlation filter,
 SMC traces, reconstruct() (:2096-2181: interpolate_nodelist, non_blurring, group1, bfs2, tree extraction) and the SWC
-export (save_nodelist :480-523).  Two builds of that one file: with the reference's frangi.h / frangi.cpp, and with the
-drop-in `class Frangi` of pnr_b200/csrc/frangi.h behind the same unchanged call site.  The comparison is on every file
-the plugin writes (with its intermediate-result switch on, and the single-tree export on -- with the defaults
-reconstruct() writes no final SWC at all)."""
+export (save_nodelist :480-523).  Three builds of that one file: with the reference's frangi.h / frangi.cpp; with the
+drop-in `class Frangi` of pnr_b200/csrc/frangi.h behind the same unchanged call site; and with a frangi3d that hands back
+arrays the test supplies (filter outputs captured on the GPU box, or the reference's own with some eigenvector signs
+turned), which brings the comparison to a host without a GPU.  The comparison is on every file the plugin writes (with its
+intermediate-result switch on, and the single-tree export on -- with the defaults reconstruct() writes no final SWC at
+all).  What it finds: the drop-in differs from the reference through the SIGN of the eigenvector and
+through nothing else; tests/test_reference_direction.py runs the drop-in with the reference's signs
+(FRANGI_GPU_FLAG_REFERENCE_DIRECTION) and gets the reference's files, all of them."""
 import os
 import subprocess
 
