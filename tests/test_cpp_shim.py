@@ -95,6 +95,24 @@ def test_every_frangi_member_of_the_plugin_links_and_eigen_is_bit_identical(memb
     assert np.array_equal(out[4, 9:], [1, -2, 3])
 
 
+def test_device_instantiation_of_the_reference_solver_on_the_host_is_bit_identical(tmp_path):
+    """pnr_b200/csrc/ref_eigen.h with T = rdouble -- the very instantiation the device pass of
+    FRANGI_GPU_FLAG_REFERENCE_DIRECTION runs -- compiled by nvcc for the host (rdouble's operators = plain IEEE double
+    operations; on the device the round-to-nearest intrinsics, the same roundings): vectors, signs and values equal the
+    compiled reference's on the eigen fixture."""
+    nvcc = "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not present")
+    exe = str(tmp_path / "ref_eigen_rdouble")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "pnr_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "cpp", "ref_eigen_rdouble.cu"), "-o", exe], check=True, capture_output=True)
+    g = np.load(os.path.join(GOLD, "case_c_eigen.npz"))
+    A = np.ascontiguousarray(g["A"], np.float64)
+    out = np.frombuffer(_pipe(exe, [len(A)], A.tobytes()), np.float64).reshape(len(A), 12)
+    assert np.array_equal(out[:, :9].reshape(-1, 3, 3), g["V"])
+    assert np.array_equal(out[:, 9:], g["d"])
+
+
 def test_host_helpers_match_the_reference(members):
     g = np.load(os.path.join(GOLD, "case_g_cold.npz"))
     t3 = np.frombuffer(_pipe(members, ["dirs3", 90], b""), np.float32).reshape(-1, 3)
