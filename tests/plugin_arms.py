@@ -154,6 +154,7 @@ if __name__ == "__main__":
     t0 = time.time()
     rp = os.path.join(workdir, "_replay.npy")
     files = p.run(I, workdir, params=sys.argv[5:], max_traces=max_traces,
+                  single_tree=os.environ.get("PNR_PLUGIN_SINGLE_TREE", "1") != "0",
                   replay=tuple(np.load(rp)) if arm == "replay" else None)
     dt = time.time() - t0
     with open(os.path.join(workdir, "_result.json"), "w") as f:

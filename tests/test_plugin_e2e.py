@@ -52,6 +52,11 @@ def test_whole_plugin_runs_qt_free_and_is_reproducible(reference, oracle):
     # the header of the final SWC carries the parameters the plugin parsed (Advantra_plugin.cpp:2283-2307)
     head = a["files"][FINAL]
     assert "#neuritesigmas=2,4,6" in head and "#ni=60" in head and "#MAX_TRACE_COUNT=3" in head
+    # with the plugin's own defaults (ENFORCE_SINGLE_TREE = false, Advantra_plugin.cpp:81) reconstruct() writes NO final SWC:
+    # the export block sits inside `if (ENFORCE_SINGLE_TREE)` (:2142-2166) -- the unmodified file shows it
+    c = run_arm("ref", I, params, 3, env=dict(PNR_PLUGIN_SINGLE_TREE="0"))
+    assert FINAL not in c["files"] and "_n2tree_.swc" in c["files"]
+    assert c["files"]["_n0_.swc"] == a["files"]["_n0_.swc"]
     # against the restated call site
     if reference.has_trace:
         r = reference.frangi3d(I, [2.0, 4.0, 6.0])
